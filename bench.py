@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- QB3 encode/decode raw-pixel GB/s on B200 (BASELINE.json metric).
+
+A step is one pass of the hot path over one batch of synthetic tiles resident in HBM: encode every tile
+(qb3cu_encode_batch), then decode every stream (qb3cu_decode_batch). Workload at any N: BASELINE config 2,
+4096 tiles of 512x512x3 u8 per GPU, QB3M_FTL lossless (weak scaling: tiles are independent, every rank gets
+its own 4096, no collective on the data path). value = raw pixel bytes of all ranks / max-over-ranks step time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tiles T] [--workload c2|c3base|c3best]
+
+--impl reference times the reference's own CPU codec (oracle/_ref/libQB3ref.so, compiled from /root/reference)
+tile-parallel on all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (w, h, bands, dtype code, numpy dtype name, mode, cband, description)
+    "c2": (512, 512, 3, 0, "uint8", 8, None, "4096 tiles 512x512x3 u8, QB3M_FTL lossless, encode+decode"),
+    "c3base": (512, 512, 8, 2, "uint16", 4, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BASE, encode+decode"),
+    "c3best": (512, 512, 8, 2, "uint16", 7, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BEST, encode+decode"),
+}
+DEFAULT_TILES = {"c2": 4096, "c3base": 1024, "c3best": 1024}
+
+
+def device_synth_tiles(ntiles, w, h, bands, dtype_code, device, t0=0, seed=12345, chunk=64):
+    """BASELINE.md section 3 generator on the device, bit-identical to tests/helpers.synth_tiles.
+    Returns a uint8 tensor [ntiles, tile_bytes] (little endian values)."""
+    import torch
+    ts = (1, 1, 2, 2, 4, 4, 8, 8)[dtype_code]
+    bits = 8 * ts
+    nb = {1: 3, 2: 6, 4: 8, 8: 10}[ts]
+    A = (1 << 40) if bits == 64 else (1 << (bits - 1)) - 1
+    out = torch.empty((ntiles, w * h * bands * ts), dtype=torch.uint8, device=device)
+    i64 = torch.int64
+
+    def lsr(x, k):  # logical shift right on int64
+        return (x >> k) & ((1 << (64 - k)) - 1)
+
+    def c64(v):  # python int -> wrapped int64 constant
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def tri(u, P, a):
+        m = u % P
+        return torch.minimum(m, P - m) * a // (P // 2)
+
+    y = torch.arange(h, device=device, dtype=i64)[None, :, None, None]
+    x = torch.arange(w, device=device, dtype=i64)[None, None, :, None]
+    c = torch.arange(bands, device=device, dtype=i64)[None, None, None, :]
+    for s in range(0, ntiles, chunk):
+        n = min(chunk, ntiles - s)
+        t = torch.arange(t0 + s, t0 + s + n, device=device, dtype=i64)[:, None, None, None]
+        v = tri(x + 37 * t, 211, A // 2) + tri(y + 91 * t, 157, A // 2) + (c * A) // (8 * bands)
+        idx = ((t * h + y) * w + x) * bands + c
+        z = (idx ^ seed) + c64(0x9E3779B97F4A7C15)
+        z = (z ^ lsr(z, 30)) * c64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * c64(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        v = v + (z & ((1 << nb) - 1))
+        if ts == 1:
+            out[s:s + n] = (v & 0xFF).to(torch.uint8).reshape(n, -1)
+        elif ts == 8:
+            out[s:s + n] = v.contiguous().view(torch.uint8).reshape(n, -1)
+        else:  # wrap into the signed torch type of the same width, then reinterpret the bytes
+            lo = v & ((1 << bits) - 1)
+            lo = torch.where(lo >= (1 << (bits - 1)), lo - (1 << bits), lo)
+            out[s:s + n] = lo.to(torch.int16 if ts == 2 else torch.int32).contiguous().view(torch.uint8).reshape(n, -1)
+        del v, idx, z
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report it instead of inventing numbers
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference_arm(args, wl):
+    """The reference CPU codec, tile-parallel on the host cores (rank 0 only)."""
+    import numpy as np
+    from helpers import REF_SO, REFBENCH_SO, synth_tiles
+    w, h, bands, dcode, dname, mode, cband, desc = WORKLOADS[wl]
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    if not (os.path.exists(REF_SO) and os.path.exists(REFBENCH_SO)):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built in the build container"}))
+        return
+    ncores = len(os.sched_getaffinity(0))
+    ntiles = args.ref_tiles
+    tiles = synth_tiles(ntiles, w, h, bands, np.dtype(dname))
+    tile_bytes = tiles[0].nbytes
+    bench = C.CDLL(REFBENCH_SO)
+    bench.refbench_run.restype = C.c_int
+    bench.refbench_run.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    slot = 1024 + int(tile_bytes * 1.14) + 64
+    streams = np.zeros((ntiles, slot), np.uint8)
+    sizes = np.zeros(ntiles, np.uint64)
+    cb = (C.c_size_t * 256)(*cband) if cband else None
+    times = []
+    for i in range(args.warmup + args.steps):
+        e, d = C.c_double(), C.c_double()
+        rc = bench.refbench_run(REF_SO.encode(), ntiles, w, h, bands, dcode, mode, cb, 1, tiles.ctypes.data,
+                                streams.ctypes.data, slot, sizes.ctypes.data, None, ncores, 1, C.byref(e), C.byref(d))
+        if rc:
+            print(json.dumps({"impl": "reference", "unavailable": "refbench_run failed rc=%d" % rc}))
+            return
+        if i >= args.warmup:
+            times.append((e.value, d.value))
+    te = sum(t[0] for t in times) / len(times)
+    td = sum(t[1] for t in times) / len(times)
+    raw = ntiles * tile_bytes
+    val = raw / (te + td) / 1e9
+    sample = "%d of the workload's tiles per step, one handle per tile, std::thread pool over tiles" % ntiles
+    print(json.dumps({
+        "impl": "reference", "metric": "QB3 encode+decode raw-pixel GB/s", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (te + td), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8" if dcode < 2 else dname, "data": "synthetic",
+        "config": {"workload": desc, "tiles_per_step": ntiles},
+        "encode_gbs": raw / te / 1e9, "decode_gbs": raw / td / 1e9,
+        "compressed_ratio": float(sizes.sum()) / raw,
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": ncores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(wl, ntiles=256):
+    """Bounded CPU sample for the main arm's cpu_baseline object (rank 0, N=1)."""
+    import numpy as np
+    from helpers import REF_SO, REFBENCH_SO, synth_tiles
+    w, h, bands, dcode, dname, mode, cband, desc = WORKLOADS[wl]
+    if not (os.path.exists(REF_SO) and os.path.exists(REFBENCH_SO)):
+        return None
+    ncores = len(os.sched_getaffinity(0))
+    tiles = synth_tiles(ntiles, w, h, bands, np.dtype(dname))
+    tile_bytes = tiles[0].nbytes
+    bench = C.CDLL(REFBENCH_SO)
+    bench.refbench_run.restype = C.c_int
+    bench.refbench_run.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_uint64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    slot = 1024 + int(tile_bytes * 1.14) + 64
+    streams = np.zeros((ntiles, slot), np.uint8)
+    sizes = np.zeros(ntiles, np.uint64)
+    cb = (C.c_size_t * 256)(*cband) if cband else None
+    e, d = C.c_double(), C.c_double()
+    reps = 3
+    rc = bench.refbench_run(REF_SO.encode(), ntiles, w, h, bands, dcode, mode, cb, 1, tiles.ctypes.data, streams.ctypes.data,
+                            slot, sizes.ctypes.data, None, ncores, reps, C.byref(e), C.byref(d))
+    if rc:
+        return None
+    raw = ntiles * tile_bytes
+    return {"value": raw / (e.value + d.value) / 1e9, "unit": "GB/s", "cores": ncores, "kind": "reference",
+            "encode_gbs": raw / e.value / 1e9, "decode_gbs": raw / d.value / 1e9,
+            "sample": "%d tiles of the workload, best of %d, one handle per tile, thread pool over tiles" % (ntiles, reps)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--tiles", type=int, default=0, help="tiles per GPU (default: the workload's)")
+    ap.add_argument("--ref-tiles", type=int, default=512, help="tiles per step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    wl = args.workload
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import torch
+    import qb3_b200 as q
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, h, bands, dcode, dname, mode, cband, desc = WORKLOADS[wl]
+    ntiles = args.tiles or DEFAULT_TILES[wl]
+    ts = q.TYPESIZE[dcode]
+    tile_bytes = w * h * bands * ts
+    cfg = q.config(w, h, bands, dcode, mode=mode, cband=cband)
+    slot = q.slot_bytes(cfg)
+
+    # every rank owns its own contiguous shard of the tile sequence (weak scaling, no exchange)
+    src = device_synth_tiles(ntiles, w, h, bands, dcode, dev, t0=rank * ntiles)
+    dst = torch.empty((ntiles, slot), dtype=torch.uint8, device=dev)
+    sizes = torch.empty(ntiles, dtype=torch.int64, device=dev)
+    est = torch.empty(ntiles, dtype=torch.int32, device=dev)
+    dstat = torch.empty(ntiles, dtype=torch.int32, device=dev)
+    out = torch.empty((ntiles, tile_bytes), dtype=torch.uint8, device=dev)
+    offsets = torch.arange(ntiles, device=dev, dtype=torch.int64) * slot
+
+    def step(events=None):
+        if events:
+            events[0].record()
+        q.encode_batch(cfg, src, ntiles, dst=dst, sizes=sizes, status=est)
+        if events:
+            events[1].record()
+        q.decode_batch(cfg, dst, offsets, sizes, ntiles, out=out, status=dstat)
+        if events:
+            events[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    assert not est.any().item() and not dstat.any().item(), "tile status reports an error"
+    assert torch.equal(out, src), "decode(encode(x)) != x"
+    comp_bytes = int(sizes.sum().item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = q.kernel_launches()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(evs[i])
+    t_end.record()
+    barrier()
+    launches = q.kernel_launches() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    total_ms = t_start.elapsed_time(t_end)
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    if world > 1:
+        t = torch.tensor([total_ms, enc_ms, dec_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, enc_ms, dec_ms = t.tolist()
+        cb = torch.tensor([comp_bytes], device=dev, dtype=torch.int64)
+        dist.all_reduce(cb)
+        comp_all = int(cb.item())
+    else:
+        comp_all = comp_bytes
+    ms_per_step = total_ms / args.steps
+    raw_rank = ntiles * tile_bytes
+    raw_all = raw_rank * world
+    value = raw_all / (ms_per_step * 1e-3) / 1e9
+
+    # end to end through the C ABI with host buffers: pinned host pixels -> device -> streams back to the host,
+    # then streams -> device -> pixels back to the host; all copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        n2 = min(ntiles, 1024)
+        h_src = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
+        h_src.copy_(src[:n2])
+        h_dst = torch.empty((n2, slot), dtype=torch.uint8).pin_memory()
+        h_sizes = torch.empty(n2, dtype=torch.int64).pin_memory()
+        h_out = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
+        d_src, d_dst, d_out = src[:n2], dst[:n2], out[:n2]
+
+        def e2e_step():
+            d_src.copy_(h_src, non_blocking=True)
+            q.encode_batch(cfg, d_src, n2, dst=d_dst, sizes=sizes[:n2], status=est[:n2])
+            h_sizes.copy_(sizes[:n2], non_blocking=True)
+            h_dst.copy_(d_dst, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            d_dst.copy_(h_dst, non_blocking=True)
+            q.decode_batch(cfg, d_dst, offsets[:n2], sizes[:n2], n2, out=d_out, status=dstat[:n2])
+            h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k2 = max(3, args.steps // 2)
+        for _ in range(k2):
+            e2e_step()
+        barrier()
+        t_e2e = (time.perf_counter() - t0) / k2
+        if world > 1:
+            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = tt.item()
+        assert torch.equal(h_out, h_src)
+        e2e = {"value": n2 * tile_bytes * world / t_e2e / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": n2 * tile_bytes + n2 * slot, "d2h_bytes_per_step": n2 * slot + n2 * tile_bytes + 8 * n2,
+               "tiles_per_step": n2, "note": "pinned host buffers; slots copied whole (not compacted)"}
+        # restore the device state for anything that follows
+        step()
+        barrier()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        enc_bytes = raw_rank + comp_bytes
+        enc_gbs_hbm = enc_bytes / (enc_ms * 1e-3) / 1e9
+        dec_gbs_hbm = enc_bytes / (dec_ms * 1e-3) / 1e9
+        dominant = "encode_kernel" if enc_ms >= dec_ms else "parse_kernel+finish_kernel"
+        dom_ach = enc_gbs_hbm if enc_ms >= dec_ms else dec_gbs_hbm
+        line = {
+            "metric": "QB3 encode+decode raw-pixel GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8" if ts == 1 else dname, "data": "synthetic",
+            "config": {"workload": desc, "tiles_per_gpu": ntiles, "tile": [w, h, bands], "mode": mode,
+                       "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (raw_rank / 1e9),
+                       "sharding": "contiguous tile ranges per rank, no collective"},
+            "encode_gbs": raw_all / (enc_ms * 1e-3) / 1e9, "decode_gbs": raw_all / (dec_ms * 1e-3) / 1e9,
+            "encode_ms": enc_ms, "decode_ms": dec_ms, "compressed_ratio": comp_all / raw_all,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_ach, "peak": peak, "unit": "GB/s",
+                         "frac": dom_ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": enc_bytes,
+                         "encode": {"achieved": enc_gbs_hbm, "frac": enc_gbs_hbm / peak},
+                         "decode": {"achieved": dec_gbs_hbm, "frac": dec_gbs_hbm / peak}},
+            "gpu_launches": int(launches), "clocks": sampler.result(), "e2e": e2e,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

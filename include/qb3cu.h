@@ -1,0 +1,115 @@
+/*
+ * qb3cu.h -- batched device-pointer C ABI of the B200-native QB3 codec.
+ *
+ * These are the entry points a host language binds (cgo / JNI / ctypes) when it already has
+ * tiles in GPU memory; the QB3.h functions are batch-of-one wrappers over them. Plain C types
+ * only: device pointers are void*, the stream is the cudaStream_t handle passed as void*
+ * (NULL = the legacy default stream). Every call is asynchronous with respect to the host and
+ * enqueues its kernels on that stream; results are in device memory.
+ *
+ * What each one replaces in the reference:
+ *   qb3cu_encode_batch  <- one qb3_encode call per tile (QB3encode.cpp:488-574), i.e. the loops
+ *                          QB3::encode_fast / encode_best (QB3encode.h:376-451, 617-724), the header
+ *                          writer (QB3encode.cpp:189-268), quantize (:151-186), the small-image
+ *                          reorder (:351-389), RLE0 (:280-332) and the stored fallback (:461-485)
+ *   qb3cu_decode_batch  <- one qb3_read_start + qb3_read_info + qb3_read_data per tile
+ *                          (QB3decode.cpp:130-264, 380-464), i.e. QB3::decode / decodeFTL
+ *                          (QB3decode.h:293-741), deRLE0 (QB3decode.cpp:267-307), dequantize (:77-107)
+ *   qb3cu_max_encoded_size <- qb3_max_encoded_size (QB3encode.cpp:112-118)
+ *
+ * There is no CPU implementation behind these: without a CUDA device they return QB3CU_ERR_CUDA.
+ */
+#ifndef QB3_B200_QB3CU_H
+#define QB3_B200_QB3CU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if !defined(LIBQB3_EXPORT)
+#if defined(__GNUC__)
+#define LIBQB3_EXPORT __attribute__((visibility("default")))
+#else
+#define LIBQB3_EXPORT
+#endif
+#endif
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define QB3CU_MAXBANDS 256
+
+/* return codes of the host-side calls */
+enum {
+    QB3CU_OK = 0,
+    QB3CU_ERR_PARAM = 1,   /* bad geometry, type, mode, band map, pitch or alignment */
+    QB3CU_ERR_CUDA = 2     /* no device / CUDA runtime failure; see qb3cu_last_cuda_error */
+};
+
+/* per tile status words written by the kernels */
+enum {
+    QB3CU_TILE_OK = 0,
+    QB3CU_TILE_BAD_HEADER = 1,   /* decode: not a QB3 stream, or it does not match the expected geometry */
+    QB3CU_TILE_CORRUPT = 2,      /* decode: the reference's failure conditions (QB3decode.h:642,665,683,703,740) */
+    QB3CU_TILE_RLE_TOO_BIG = 3   /* decode: expanded RLE payload larger than the raw size (QB3decode.cpp:401) */
+};
+
+/* Settings shared by all tiles of a batch: what the reference keeps in struct encs (QB3common.h:68-88). */
+typedef struct qb3cu_config {
+    uint32_t width, height, bands; /* 1..65536, 1..65536, 1..256 */
+    uint32_t dtype;                /* qb3_dtype */
+    uint32_t mode;                 /* qb3_mode as a caller would request it: 0..8 */
+    uint32_t away;                 /* quantisation rounds half away from zero */
+    uint64_t quanta;               /* >= 1; 1 = lossless */
+    uint64_t order;                /* 4x4 scan curve, 0 = the mode's default (Hilbert, Z for modes 0..3) */
+    uint64_t stride;               /* line to line distance in values, 0 = width * bands */
+    uint8_t cband[QB3CU_MAXBANDS]; /* cband[c] = band subtracted from band c, c itself for none */
+} qb3cu_config;
+
+/* Fills width/height/bands/dtype and the reference defaults: FTL, quanta 1, identity band map or
+   {1,1,1[,3]} for 3 or 4 bands (QB3encode.cpp:36-45). Returns QB3CU_ERR_PARAM for bad arguments. */
+LIBQB3_EXPORT int qb3cu_config_init(qb3cu_config *cfg, uint32_t width, uint32_t height, uint32_t bands, uint32_t dtype);
+
+/* Identical to qb3_max_encoded_size for the same geometry. */
+LIBQB3_EXPORT size_t qb3cu_max_encoded_size(const qb3cu_config *cfg);
+
+/* Bytes to reserve per tile in the destination of qb3cu_encode_batch: the value above rounded up
+   for 16-byte vector stores plus one spare vector. Slots must start 16-byte aligned. */
+LIBQB3_EXPORT size_t qb3cu_slot_bytes(const qb3cu_config *cfg);
+
+/*
+ * Encodes ntiles independent tiles, one QB3 stream each, byte-identical to qb3_encode.
+ *   d_src            tile t starts at d_src + t * src_tile_pitch bytes; row major, band interleaved
+ *   d_dst            stream t is written at d_dst + t * dst_slot_bytes (>= qb3cu_slot_bytes, multiple of 16)
+ *   d_sizes[t]       stream length in bytes
+ *   d_status[t]      QB3CU_TILE_OK, may be NULL
+ *   d_state          NULL, or ntiles * 3 * bands uint64: per band {prev, runbits, cf} read before and written
+ *                    after each tile -- the running state the reference keeps in the handle (QB3common.h:63)
+ */
+LIBQB3_EXPORT int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch,
+                                     void *d_dst, size_t dst_slot_bytes, uint64_t *d_sizes, uint32_t *d_status,
+                                     uint64_t *d_state, size_t ntiles, void *stream);
+
+/*
+ * Decodes ntiles streams whose headers must all describe width x height x bands of dtype (cfg->mode,
+ * quanta, order and cband are read from each stream's own header, cfg->stride is the output stride).
+ *   d_streams        base pointer; stream t occupies [d_offsets[t], d_offsets[t] + d_lens[t])
+ *   d_dst            tile t is written at d_dst + t * dst_tile_pitch bytes
+ *   d_status[t]      QB3CU_TILE_* ; the tile content is undefined unless QB3CU_TILE_OK
+ *   ref_compat       nonzero: a stream without a CB chunk decodes with an all-zero band map, as the
+ *                    reference decoder does; zero: identity map, as the format specifies
+ */
+LIBQB3_EXPORT int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,
+                                     const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch,
+                                     uint32_t *d_status, int ref_compat, size_t ntiles, void *stream);
+
+/* cudaError_t of the most recent failing CUDA call made by this library on the calling thread. */
+LIBQB3_EXPORT int qb3cu_last_cuda_error(void);
+
+/* Number of kernels this library has launched since load (all threads); for benchmark bookkeeping. */
+LIBQB3_EXPORT uint64_t qb3cu_kernel_launches(void);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* QB3_B200_QB3CU_H */

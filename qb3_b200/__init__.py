@@ -1,0 +1,131 @@
+"""qb3_b200 -- thin ctypes binding of libQB3.so (QB3.h API + qb3cu.h batched C ABI).
+
+The product is the shared library built from qb3_b200/csrc (hand-written CUDA for sm_100a behind a C
+ABI); this module only loads it and passes device pointers of torch tensors through. There is no
+Python or CPU implementation of the codec here: if the library is missing, loading fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libQB3.so")
+
+MAXBANDS = 256
+U8, I8, U16, I16, U32, I32, U64, I64 = range(8)
+TYPESIZE = (1, 1, 2, 2, 4, 4, 8, 8)
+M_BASE_Z, M_CF, M_RLE, M_CF_RLE, M_BASE, M_CF_H, M_RLE_H, M_BEST, M_FTL = range(9)
+M_STORED = 255
+TILE_OK, TILE_BAD_HEADER, TILE_CORRUPT, TILE_RLE_TOO_BIG = range(4)
+
+
+class Config(C.Structure):
+    """struct qb3cu_config (include/qb3cu.h)."""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("bands", C.c_uint32), ("dtype", C.c_uint32),
+                ("mode", C.c_uint32), ("away", C.c_uint32), ("quanta", C.c_uint64), ("order", C.c_uint64),
+                ("stride", C.c_uint64), ("cband", C.c_uint8 * MAXBANDS)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, sz, u64p, u32p = C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p
+        cfgp = C.POINTER(Config)
+        L.qb3cu_config_init.restype, L.qb3cu_config_init.argtypes = C.c_int, [cfgp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.qb3cu_max_encoded_size.restype, L.qb3cu_max_encoded_size.argtypes = sz, [cfgp]
+        L.qb3cu_slot_bytes.restype, L.qb3cu_slot_bytes.argtypes = sz, [cfgp]
+        L.qb3cu_encode_batch.restype = C.c_int
+        L.qb3cu_encode_batch.argtypes = [cfgp, vp, sz, vp, sz, u64p, u32p, u64p, sz, vp]
+        L.qb3cu_decode_batch.restype = C.c_int
+        L.qb3cu_decode_batch.argtypes = [cfgp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz, vp]
+        L.qb3cu_last_cuda_error.restype, L.qb3cu_last_cuda_error.argtypes = C.c_int, []
+        L.qb3cu_kernel_launches.restype, L.qb3cu_kernel_launches.argtypes = C.c_uint64, []
+        _lib = L
+    return _lib
+
+
+def config(width, height, bands, dtype, mode=M_FTL, cband=None, quanta=1, away=False, order=0, stride=0):
+    """qb3cu_config with the reference defaults (FTL, identity or RGB band map) unless overridden."""
+    cfg = Config()
+    if lib().qb3cu_config_init(C.byref(cfg), width, height, bands, dtype) != 0:
+        raise ValueError("bad geometry or type")
+    cfg.mode, cfg.quanta, cfg.away, cfg.order, cfg.stride = mode, quanta, int(away), order, stride
+    if cband is not None:
+        if len(cband) != bands:
+            raise ValueError("band map length")
+        for i, b in enumerate(cband):
+            cfg.cband[i] = b
+    return cfg
+
+
+def max_encoded_size(cfg):
+    return lib().qb3cu_max_encoded_size(C.byref(cfg))
+
+
+def slot_bytes(cfg):
+    return lib().qb3cu_slot_bytes(C.byref(cfg))
+
+
+def kernel_launches():
+    return lib().qb3cu_kernel_launches()
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: rc=%d cuda=%d" % (what, rc, lib().qb3cu_last_cuda_error()))
+
+
+def _stream_handle(stream):
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+def encode_batch(cfg, src, ntiles, dst=None, sizes=None, status=None, state=None, tile_pitch=None, stream=None):
+    """Encode ntiles tiles resident on the GPU. src: torch tensor holding the tiles back to back
+    (tile_pitch bytes apart, default one compact tile). Returns (dst uint8 [ntiles, slot], sizes uint64-as-int64 [ntiles],
+    status int32 [ntiles]); asynchronous on the given / current torch stream."""
+    import torch
+    slot = slot_bytes(cfg)
+    dev = src.device
+    if tile_pitch is None:
+        tile_pitch = cfg.width * cfg.height * cfg.bands * TYPESIZE[cfg.dtype] if not cfg.stride else \
+            cfg.stride * cfg.height * TYPESIZE[cfg.dtype]
+    if dst is None:
+        dst = torch.empty((ntiles, slot), dtype=torch.uint8, device=dev)
+    if sizes is None:
+        sizes = torch.empty((ntiles,), dtype=torch.int64, device=dev)
+    if status is None:
+        status = torch.empty((ntiles,), dtype=torch.int32, device=dev)
+    rc = lib().qb3cu_encode_batch(C.byref(cfg), src.data_ptr(), tile_pitch, dst.data_ptr(), dst.stride(0),
+                                  sizes.data_ptr(), status.data_ptr(), state.data_ptr() if state is not None else None,
+                                  ntiles, _stream_handle(stream))
+    _check(rc, "qb3cu_encode_batch")
+    return dst, sizes, status
+
+
+def decode_batch(cfg, streams, offsets, lens, ntiles, out=None, status=None, ref_compat=False, tile_pitch=None,
+                 out_dtype=None, stream=None):
+    """Decode ntiles streams resident on the GPU. streams: uint8 tensor; offsets, lens: int64 tensors [ntiles] (bytes).
+    Returns (out, status)."""
+    import torch
+    ts = TYPESIZE[cfg.dtype]
+    if tile_pitch is None:
+        tile_pitch = (cfg.stride if cfg.stride else cfg.width * cfg.bands) * cfg.height * ts
+    dev = streams.device
+    if out is None:
+        out = torch.empty((ntiles, tile_pitch), dtype=torch.uint8, device=dev)
+    if status is None:
+        status = torch.empty((ntiles,), dtype=torch.int32, device=dev)
+    rc = lib().qb3cu_decode_batch(C.byref(cfg), streams.data_ptr(), offsets.data_ptr(), lens.data_ptr(), out.data_ptr(),
+                                  tile_pitch, status.data_ptr(), int(ref_compat), ntiles, _stream_handle(stream))
+    _check(rc, "qb3cu_decode_batch")
+    return out, status

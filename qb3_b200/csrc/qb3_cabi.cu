@@ -1,0 +1,231 @@
+/*
+ * qb3_cabi.cu -- the batched C ABI declared in include/qb3cu.h: argument checking, header bytes,
+ * launch geometry. No pixel or bit work happens on the host.
+ */
+#include <atomic>
+#include <cstring>
+
+#include "qb3_device.cuh"
+
+namespace qb3 {
+cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st);
+cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st);
+
+static thread_local int g_last_cuda_error = 0;
+static std::atomic<uint64_t> g_launches(0);
+
+static const uint32_t TYPESIZE[8] = {1, 1, 2, 2, 4, 4, 8, 8};
+
+int note_cuda(cudaError_t e)
+{
+    if (e == cudaSuccess) return QB3CU_OK;
+    g_last_cuda_error = (int)e;
+    return QB3CU_ERR_CUDA;
+}
+void count_launches(uint64_t n) { g_launches += n; }
+
+static bool rle_requested(uint32_t mode) { return mode == 2 || mode == 3 || mode == 6 || mode == 7; }
+
+static bool geometry_ok(const qb3cu_config *c)
+{
+    return c && c->width >= 1 && c->width <= 0x10000 && c->height >= 1 && c->height <= 0x10000
+        && c->bands >= 1 && c->bands <= QB3CU_MAXBANDS && c->dtype <= 7;
+}
+
+/* Header bytes up to and including "DT" (reference: QB3encode.cpp:189-268, doc/QB3.md:228-259) */
+static uint32_t build_headers(const qb3cu_config *c, uint32_t mode_byte, uint64_t order, uint8_t *out)
+{
+    uint32_t n = 0;
+    auto put = [&](uint64_t v, uint32_t bytes) { for (uint32_t i = 0; i < bytes; i++) out[n++] = (uint8_t)(v >> (8 * i)); };
+    put(0x80334251u, 4); /* "QB3\200" */
+    put(c->width - 1, 2);
+    put(c->height - 1, 2);
+    put(c->bands - 1, 1);
+    put(c->dtype, 1);
+    put(mode_byte, 1);
+    bool banddiff = false;
+    for (uint32_t b = 0; b < c->bands; b++) banddiff |= c->cband[b] != b;
+    if (mode_byte != M_STORED && banddiff) {
+        put('C' | ('B' << 8), 2);
+        put(c->bands, 2);
+        for (uint32_t b = 0; b < c->bands; b++) put(c->cband[b], 1);
+    }
+    if (c->quanta >= 2) {
+        const uint32_t qbytes = 1 + topbit64(c->quanta) / 8;
+        put('Q' | ('V' << 8), 2);
+        put(qbytes, 2);
+        put(c->quanta, qbytes);
+    }
+    if (order != ZCURVE && mode_byte != M_STORED) {
+        put('S' | ('C' << 8), 2);
+        put(8, 2);
+        put(order, 8);
+    }
+    put('D' | ('T' << 8), 2);
+    return n;
+}
+} // namespace qb3
+
+using namespace qb3;
+
+extern "C" {
+
+int qb3cu_config_init(qb3cu_config *cfg, uint32_t width, uint32_t height, uint32_t bands, uint32_t dtype)
+{
+    if (!cfg) return QB3CU_ERR_PARAM;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->width = width; cfg->height = height; cfg->bands = bands; cfg->dtype = dtype;
+    if (!geometry_ok(cfg)) return QB3CU_ERR_PARAM;
+    cfg->mode = M_FTL;
+    cfg->quanta = 1;
+    for (uint32_t c = 0; c < bands; c++) cfg->cband[c] = (uint8_t)c;
+    if (bands == 3 || bands == 4) cfg->cband[0] = cfg->cband[2] = 1;
+    return QB3CU_OK;
+}
+
+size_t qb3cu_max_encoded_size(const qb3cu_config *cfg)
+{
+    if (!geometry_ok(cfg)) return 0;
+    /* same expression, in double, as the reference (QB3encode.cpp:112-118): it also gates the RLE pass */
+    const size_t n = (size_t)16 * ((cfg->width + 3) / 4) * ((cfg->height + 3) / 4) * cfg->bands;
+    const double bits_per_value = 17.0 / 16.0 + 8 * TYPESIZE[cfg->dtype];
+    return 1024 + static_cast<size_t>(bits_per_value * n / 8);
+}
+
+size_t qb3cu_slot_bytes(const qb3cu_config *cfg)
+{
+    const size_t m = qb3cu_max_encoded_size(cfg);
+    return m ? ((m + 15) & ~(size_t)15) + 16 : 0;
+}
+
+int qb3cu_last_cuda_error(void) { return g_last_cuda_error; }
+uint64_t qb3cu_kernel_launches(void) { return g_launches.load(); }
+
+int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch, void *d_dst,
+                       size_t dst_slot_bytes, uint64_t *d_sizes, uint32_t *d_status, uint64_t *d_state,
+                       size_t ntiles, void *stream)
+{
+    if (!geometry_ok(cfg) || cfg->mode > M_FTL || cfg->quanta < 1 || !d_src || !d_dst || !d_sizes) return QB3CU_ERR_PARAM;
+    if (ntiles == 0) return QB3CU_OK;
+    if (ntiles > 0x7fffffffull) return QB3CU_ERR_PARAM;
+    if (cfg->mode != 0 && cfg->mode != 4 && cfg->mode != 8) return QB3CU_ERR_PARAM; /* TODO(best, rle): not on the device yet */
+    const uint32_t tsize = TYPESIZE[cfg->dtype], bits = 8 * tsize;
+    for (uint32_t c = 0; c < cfg->bands; c++) if (cfg->cband[c] >= cfg->bands) return QB3CU_ERR_PARAM;
+    if (((uintptr_t)d_src | src_tile_pitch) % tsize) return QB3CU_ERR_PARAM;
+    if (((uintptr_t)d_dst | dst_slot_bytes) % 16 || dst_slot_bytes < qb3cu_slot_bytes(cfg)) return QB3CU_ERR_PARAM;
+    const uint64_t line = (uint64_t)cfg->width * cfg->bands;
+    if (cfg->stride && cfg->stride < line) return QB3CU_ERR_PARAM;
+
+    EncArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = static_cast<const uint8_t *>(d_src);
+    a.src_pitch = src_tile_pitch;
+    a.dst = static_cast<uint8_t *>(d_dst);
+    a.slot = dst_slot_bytes;
+    a.sizes = reinterpret_cast<unsigned long long *>(d_sizes);
+    a.status = d_status;
+    a.state = reinterpret_cast<unsigned long long *>(d_state);
+    a.stride = cfg->stride ? cfg->stride : line;
+    a.quanta = cfg->quanta;
+    a.w = cfg->width; a.h = cfg->height; a.bands = cfg->bands;
+    a.raw_size = line * cfg->height * tsize;
+    a.max_size = qb3cu_max_encoded_size(cfg);
+    a.is_signed = cfg->dtype & 1;
+    a.away = cfg->away != 0;
+    memcpy(a.cband, cfg->cband, sizeof(a.cband));
+
+    /* mode: the RLE variants code as their base mode, RLE is a byte pass afterwards (reference: QB3encode.cpp:494-506) */
+    a.rle_mode = rle_requested(cfg->mode) ? cfg->mode : 0;
+    a.mode = a.rle_mode ? cfg->mode - 2 : cfg->mode;
+    a.order = cfg->order ? cfg->order : (cfg->mode <= 3 ? ZCURVE : HILBERT);
+    a.hdr_len = build_headers(cfg, a.mode, a.order, a.hdr);
+    a.hdr_stored_len = build_headers(cfg, M_STORED, a.order, a.hdr_stored);
+
+    /* coded geometry; images with a side under 4 are reordered into 4 wide / 4 high strips (reference: QB3encode.cpp:351-389) */
+    a.vw = a.w; a.vh = a.h;
+    if ((uint64_t)a.w * a.h <= 16) a.small = 3; /* stored outright (reference: QB3encode.cpp:490-491) */
+    else if (a.w < 4) { a.small = 1; a.vw = 4; a.vh = 4 * ((a.w * a.h + 15) / 16); }
+    else if (a.h < 4) { a.small = 2; a.vh = 4; a.vw = 4 * ((a.w * a.h + 15) / 16); }
+    a.nbx = (a.vw + 3) / 4;
+    a.nby = (a.vh + 3) / 4;
+    a.vec_stage = a.quanta == 1 && a.small == 0;
+
+    /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
+    const uint32_t max_threads = tsize <= 2 ? 512 : 256;
+    uint32_t seg_blocks = max_threads / a.bands;
+    if (seg_blocks < 1) seg_blocks = 1;
+    if (seg_blocks > a.nbx) seg_blocks = a.nbx;
+    a.segs = (a.nbx + seg_blocks - 1) / seg_blocks;
+    a.seg_blocks = (a.nbx + a.segs - 1) / a.segs;
+    a.segs = (a.nbx + a.seg_blocks - 1) / a.seg_blocks;
+    uint32_t threads = (a.seg_blocks * a.bands + 31) & ~31u;
+    if (threads > 512) return QB3CU_ERR_PARAM;
+    a.rowpitch = ((a.seg_blocks * 4 * a.bands * tsize + 15) & ~15u) + 16;
+    a.win_words = ((a.hdr_len * 8 + 128 + threads * max_group_bits(bits)) / 32 + 16 + 3) & ~3u;
+    const size_t smem = (size_t)a.win_words * 4 + 4 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4
+                      + 2 * (size_t)a.bands + threads;
+    if (smem > 200 * 1024) return QB3CU_ERR_PARAM;
+
+    cudaError_t err = launch_encode(a, tsize, ntiles, threads, smem, static_cast<cudaStream_t>(stream));
+    if (err == cudaSuccess) count_launches(1);
+    return note_cuda(err);
+}
+
+int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,
+                       const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch, uint32_t *d_status,
+                       int ref_compat, size_t ntiles, void *stream)
+{
+    if (!geometry_ok(cfg) || !d_streams || !d_offsets || !d_lens || !d_dst || !d_status) return QB3CU_ERR_PARAM;
+    if (ntiles == 0) return QB3CU_OK;
+    if (ntiles > 0x7fffffffull) return QB3CU_ERR_PARAM;
+    const uint32_t tsize = TYPESIZE[cfg->dtype];
+    if (((uintptr_t)d_dst | dst_tile_pitch) % tsize) return QB3CU_ERR_PARAM;
+    const uint64_t line = (uint64_t)cfg->width * cfg->bands;
+    if (cfg->stride && cfg->stride < line) return QB3CU_ERR_PARAM;
+    DecArgs a;
+    memset(&a, 0, sizeof(a));
+    a.streams = static_cast<const uint8_t *>(d_streams);
+    a.offsets = reinterpret_cast<const unsigned long long *>(d_offsets);
+    a.lens = reinterpret_cast<const unsigned long long *>(d_lens);
+    a.dst = static_cast<uint8_t *>(d_dst);
+    a.dst_pitch = dst_tile_pitch;
+    a.status = d_status;
+    a.stride = cfg->stride ? cfg->stride : line;
+    a.w = cfg->width; a.h = cfg->height; a.bands = cfg->bands; a.dtype = cfg->dtype;
+    a.ref_compat = ref_compat != 0;
+    a.ntiles = (uint32_t)ntiles;
+    cudaError_t err = launch_decode(a, tsize, static_cast<cudaStream_t>(stream));
+    if (err == cudaSuccess) count_launches(2);
+    return note_cuda(err);
+}
+
+/* ---- host-logic probes for the CPU-only tests: the closed forms the kernels use (qb3_codes.h) ---- */
+
+LIBQB3_EXPORT uint32_t qb3cu_debug_cs_entry(uint32_t U, uint32_t d) { return cs_entry(U, d); }
+LIBQB3_EXPORT uint32_t qb3cu_debug_cs_signal(uint32_t U) { return cs_signal(U); }
+LIBQB3_EXPORT uint32_t qb3cu_debug_ds_entry(uint32_t U, uint32_t x) { return ds_entry(U, x); }
+/* (len << 12) | bits of a stand-alone value at a rung below 11, the reference's CRG table entry */
+LIBQB3_EXPORT uint32_t qb3cu_debug_code(uint32_t rung, uint32_t v, int group)
+{
+    uint64_t lo; uint32_t hi;
+    if (rung == 0) return 0x1000u | (v & 1);
+    if (group ? group_swaps(rung) : single_swaps(rung)) v = mswap<uint32_t>(v, rung);
+    const uint32_t len = code_bits<uint32_t>(v, rung, lo, hi);
+    return (len << 12) | (uint32_t)lo;
+}
+LIBQB3_EXPORT uint32_t qb3cu_debug_decode(uint32_t rung, uint32_t x, int group)
+{
+    uint32_t len;
+    if (rung == 0) return 0x1000u | (x & 1);
+    uint32_t v = (uint32_t)decode_bits(x, 0, rung, len);
+    if (group ? group_swaps(rung) : single_swaps(rung)) v = mswap<uint32_t>(v, rung);
+    return (len << 12) | v;
+}
+LIBQB3_EXPORT int qb3cu_debug_step(uint32_t M, int decode) { return decode ? step_decode_index(M) : step_encode_index(M); }
+LIBQB3_EXPORT uint32_t qb3cu_debug_headers(const qb3cu_config *cfg, uint32_t mode_byte, uint8_t *out)
+{
+    const uint64_t order = cfg->order ? cfg->order : (cfg->mode <= 3 ? ZCURVE : HILBERT);
+    return build_headers(cfg, mode_byte, order, out);
+}
+
+} /* extern "C" */

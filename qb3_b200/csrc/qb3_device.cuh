@@ -1,0 +1,116 @@
+/*
+ * qb3_device.cuh -- launch argument blocks and small device helpers shared by the kernels.
+ */
+#ifndef QB3_B200_DEVICE_CUH
+#define QB3_B200_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qb3_codes.h"
+#include "../../include/qb3cu.h"
+
+namespace qb3 {
+
+constexpr int MAXBANDS = 256;
+constexpr int MAXHDR = 320; /* 11 + CB(4+256) + QV(4+8) + SC(12) + DT(2) = 297 */
+
+/* Everything the encode kernel needs, passed by value as a __grid_constant__ parameter. */
+struct EncArgs {
+    const uint8_t *src;
+    uint64_t src_pitch;   /* bytes between tiles */
+    uint8_t *dst;
+    uint64_t slot;        /* bytes per destination slot, multiple of 16 */
+    unsigned long long *sizes;
+    uint32_t *status;
+    unsigned long long *state; /* optional [tile][3][bands]: prev, runbits, cf */
+    uint64_t stride;      /* source line stride in values */
+    uint64_t quanta;
+    uint64_t order;       /* scan curve actually used */
+    uint64_t raw_size;    /* w*h*bands*sizeof(T) */
+    uint64_t max_size;    /* qb3_max_encoded_size */
+    uint32_t w, h, bands; /* image geometry */
+    uint32_t vw, vh;      /* geometry being coded: the image, or its small-image reorder */
+    uint32_t small;       /* 0 none, 1 narrow (w < 4): rows concatenated, 2 short (h < 4): column major pixels */
+    uint32_t nbx, nby;    /* 4x4 blocks per row / column of the coded geometry */
+    uint32_t seg_blocks;  /* blocks handled per CTA iteration */
+    uint32_t segs;        /* iterations per block row */
+    uint32_t mode;        /* stream mode with RLE stripped: 0, 1, 4, 5 or 8 */
+    uint32_t rle_mode;    /* 0, or the RLE mode byte the caller asked for (2, 3, 6, 7) */
+    uint32_t is_signed, away;
+    uint32_t vec_stage;   /* rows can be staged with 16 byte copies (no quantisation, no reorder) */
+    uint32_t rowpitch;    /* bytes between staged rows in shared memory, multiple of 16 */
+    uint32_t win_words;   /* bit window size in 32 bit words */
+    uint32_t hdr_len, hdr_stored_len;
+    uint8_t hdr[MAXHDR];        /* headers up to and including "DT", mode byte = mode */
+    uint8_t hdr_stored[MAXHDR]; /* same for the stored fallback (mode 255, no CB / SC) */
+    uint8_t cband[MAXBANDS];
+};
+
+struct DecArgs {
+    const uint8_t *streams;
+    const unsigned long long *offsets, *lens;
+    uint8_t *dst;
+    uint64_t dst_pitch;   /* bytes between tiles */
+    uint32_t *status;
+    uint64_t stride;      /* destination line stride in values */
+    uint32_t w, h, bands, dtype;
+    uint32_t ref_compat;
+    uint32_t ntiles;
+};
+
+/* header fields of one stream, parsed on the device */
+struct StreamInfo {
+    uint64_t order, quanta;
+    uint32_t mode;
+    uint32_t data_off;    /* payload offset from the stream start */
+    uint32_t has_cb;
+    uint32_t bad;
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+/* streaming 16 byte global load, bypassing L1 allocation: every input byte is read once */
+__device__ __forceinline__ uint4 ld_stream16(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+/* streaming 16 byte global store */
+__device__ __forceinline__ void st_stream16(void *p, uint4 v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+/* CTA wide exclusive scan of one uint32 per thread; returns the prefix, total gets the sum. blockDim.x <= 1024.
+   scratch: 33 words of shared memory. Contains two __syncthreads(). */
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *scratch, uint32_t &total)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < nwarps ? scratch[lane] : 0, t = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t += o;
+        }
+        scratch[lane] = t - s; /* exclusive prefix of the warp sums */
+        if (lane == 31) scratch[32] = t;
+    }
+    __syncthreads();
+    total = scratch[32];
+    return scratch[warp] + inc - v;
+}
+
+} // namespace qb3
+#endif

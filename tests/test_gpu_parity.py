@@ -1,0 +1,226 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the
+oracle on seeded inputs, against the committed golden vectors made by the reference library, and -- at the
+BASELINE sizes -- through size independent properties (round trip, checksum of stream sizes)."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import qb3_b200 as q
+from helpers import (CONTENT_KINDS, DTYPES, MODE_BASE, MODE_BEST, MODE_FTL, PRODUCT_SO, QB3Lib, content, dtype_code,
+                     golden_cases, golden_check_stream, golden_image, golden_kwargs, oracle, synth_tiles)
+
+pytestmark = pytest.mark.gpu
+
+ENC_MODES_DONE = {0, 4, 8}  # encoder modes implemented on the device
+
+
+def product():
+    return QB3Lib(PRODUCT_SO, 256)
+
+
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch
+
+
+# ------------------------------------------------------------------ QB3.h API, single images
+
+def test_api_encode_matches_golden():
+    P = product()
+    bad = []
+    for case in golden_cases():
+        kw = golden_kwargs(case)
+        if kw.get("mode", MODE_FTL) not in ENC_MODES_DONE:
+            continue
+        try:
+            golden_check_stream(case, P.encode(golden_image(case), **kw))
+        except (AssertionError, RuntimeError) as e:
+            bad.append((case["name"], type(e).__name__))
+    assert not bad, "%d of %d golden cases differ: %s" % (len(bad), len(golden_cases()), bad[:12])
+
+
+def test_api_decode_matches_golden():
+    P, O = product(), oracle()
+    bad = []
+    for case in golden_cases():
+        if case["kind"] != "small":
+            continue
+        s = bytes.fromhex(case["stream"])
+        os.environ["QB3_REF_COMPAT"] = "1"  # decode exactly like the reference decoder
+        try:
+            d = P.decode(s)
+        finally:
+            del os.environ["QB3_REF_COMPAT"]
+        if case["ref_decoded"] is None:
+            ok = d is None
+        else:
+            ok = d is not None and hashlib.sha256(d.tobytes()).hexdigest() == case["ref_decoded"]
+        if ok and d is not None and case.get("quanta", 1) == 1:
+            d2 = P.decode(s)  # spec behaviour: identity band map by default -> the original pixels
+            ok = d2 is not None and np.array_equal(d2, golden_image(case))
+        if not ok:
+            bad.append(case["name"])
+    assert not bad, "%d golden streams decode differently: %s" % (len(bad), bad[:12])
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_api_round_trip_and_oracle_all_content(dt):
+    P, O = product(), oracle()
+    for i, kind in enumerate(CONTENT_KINDS):
+        for (w, h, b) in ((17, 9, 3), (33, 31, 1), (12, 8, 5)):
+            img = content(kind, w, h, b, dt, seed=7 * i + w)
+            for mode in (MODE_FTL, MODE_BASE, MODE_BEST, 0, 1, 2, 5):
+                if mode not in ENC_MODES_DONE:
+                    continue
+                s = P.encode(img, mode=mode)
+                assert s == O.encode(img, mode=mode), (kind, w, h, b, mode)
+                assert np.array_equal(P.decode(s), img), (kind, w, h, b, mode)
+
+
+def test_api_quanta_stride_state():
+    P, O = product(), oracle()
+    for dt in (np.uint8, np.int16, np.int32, np.uint64):
+        img = content("signed", 21, 14, 2, dt, seed=3)
+        for qv, away in ((2, False), (2, True), (3, False), (4, True), (5, False), (10, True)):
+            s = P.encode(img, mode=MODE_BASE, quanta=qv, away=away)
+            assert s == O.encode(img, mode=MODE_BASE, quanta=qv, away=away)
+            assert np.array_equal(P.decode(s), O.decode(s))
+    # strided source and destination (stride in values, QB3.h:116,147)
+    back = content("synth", 40, 12, 3, np.uint16)
+    view = np.ascontiguousarray(back.reshape(12, 120)[:, :81].reshape(12, 27, 3))
+    L = P.lib
+    e = L.qb3_create_encoder(27, 12, 3, dtype_code(np.uint16))
+    L.qb3_set_encoder_stride(e, 120)
+    dst = np.zeros(L.qb3_max_encoded_size(e), np.uint8)
+    n = L.qb3_encode(e, back.ctypes.data, dst.ctypes.data)
+    L.qb3_destroy_encoder(e)
+    s = dst[:n].tobytes()
+    assert s == O.encode(view)
+    out = P.decode(s, stride=100)
+    assert np.array_equal(out[:, :81].reshape(12, 27, 3), view) and not out[:, 81:].any()
+    # running state persists across qb3_encode calls on one handle
+    img = content("synth", 16, 16, 1, np.uint8)
+    assert P.encode(img, mode=MODE_BASE, reps=2) == O.encode(img, mode=MODE_BASE, reps=2)
+
+
+def test_api_small_and_many_bands():
+    P, O = product(), oracle()
+    for (w, h, b) in ((3, 100, 3), (1, 17, 1), (2, 9, 1), (100, 2, 3), (17, 1, 1), (1000, 3, 1), (2, 2000, 1), (5, 4, 1), (4, 4, 2), (2, 2, 1)):
+        for dt in (np.uint8, np.int32, np.uint64):
+            img = content("synth", w, h, b, dt, seed=w + h)
+            for qv in (1, 3):
+                s = P.encode(img, mode=MODE_BASE, quanta=qv)
+                assert s == O.encode(img, mode=MODE_BASE, quanta=qv), (w, h, b, qv)
+                d, od = P.decode(s), O.decode(s)
+                assert (d is None) == (od is None) and (d is None or np.array_equal(d, od)), (w, h, b, qv)
+    for bands in (17, 64, 256):
+        img = content("synth", 12, 8, bands, np.uint16)
+        s = P.encode(img, mode=MODE_BASE, cband=[0] * bands)
+        assert s == O.encode(img, mode=MODE_BASE, cband=[0] * bands)
+        assert np.array_equal(P.decode(s), img)
+
+
+def test_api_stored_fallback_and_errors():
+    P, O = product(), oracle()
+    img = content("noise", 32, 32, 1, np.uint8)
+    s = P.encode(img)
+    assert s[10] == 255 and s == O.encode(img)  # incompressible -> stored (QB3encode.cpp:570-573)
+    assert np.array_equal(P.decode(s), img)
+    assert P.decode(s + b"\x00") is None        # stored payload must be exact (QB3decode.cpp:360)
+    ok = P.encode(content("synth", 16, 16, 1, np.uint8))
+    assert P.decode(ok + b"\x00") is None       # one spare byte is an error (QB3decode.h:411)
+    assert P.decode(ok[:-1] + b"\xff\xff") is None
+
+
+# ------------------------------------------------------------------ batched C ABI
+
+def encode_tiles(tiles, **kw):
+    torch = torch_mod()
+    n, h, w, b = tiles.shape
+    cfg = q.config(w, h, b, dtype_code(tiles.dtype), **kw)
+    src = torch.from_numpy(tiles.view(np.uint8).reshape(n, -1)).cuda()
+    dst, sizes, status = q.encode_batch(cfg, src, n)
+    torch.cuda.synchronize()
+    return cfg, dst, sizes, status
+
+
+@pytest.mark.parametrize("shape,dt,kw", [
+    ((512, 512, 3), np.uint8, dict(mode=MODE_FTL)),                      # BASELINE config 2
+    ((512, 512, 8), np.uint16, dict(mode=MODE_BASE, cband=[0] * 8)),     # config 3
+    ((512, 512, 8), np.uint16, dict(mode=MODE_BEST, cband=[0] * 8)),
+    ((513, 511, 1), np.int32, dict(mode=MODE_FTL)),                      # config 4
+    ((513, 511, 1), np.uint64, dict(mode=MODE_FTL, quanta=3)),
+    ((64, 64, 16), np.uint16, dict(mode=MODE_BASE)),                     # config 5 corners
+    ((1024, 1024, 1), np.uint8, dict(mode=MODE_BASE)),
+    ((100, 60, 3), np.int8, dict(mode=MODE_FTL)),
+])
+def test_batch_encode_matches_oracle_and_round_trips(shape, dt, kw):
+    torch = torch_mod()
+    if kw.get("mode", MODE_FTL) not in ENC_MODES_DONE:
+        pytest.skip("mode not on the device yet")
+    w, h, b = shape
+    n = 6
+    tiles = synth_tiles(n, w, h, b, dt)
+    cfg, dst, sizes, status = encode_tiles(tiles, **kw)
+    sizes_h, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
+    assert not status.cpu().numpy().any()
+    O = oracle()
+    for t in range(n):
+        want = O.encode(tiles[t], **kw)
+        got = dst_h[t, :sizes_h[t]].tobytes()
+        assert got == want, "tile %d: %d vs %d bytes" % (t, len(got), len(want))
+    # decode the batch in place on the GPU
+    offsets = (torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0))
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, n)
+    torch.cuda.synchronize()
+    assert not st.cpu().numpy().any()
+    dec = out.cpu().numpy().view(tiles.dtype).reshape(tiles.shape)
+    if kw.get("quanta", 1) == 1:
+        assert np.array_equal(dec, tiles)
+    else:
+        for t in range(n):
+            assert np.array_equal(dec[t], O.decode(dst_h[t, :sizes_h[t]].tobytes()))
+
+
+def test_batch_full_size_properties():
+    """BASELINE config 2 at full size: 4096 tiles of 512x512x3 u8. Every tile must round trip, and the
+    sizes of a deterministic sample must equal the oracle's."""
+    torch = torch_mod()
+    n, w, h, b = 4096, 512, 512, 3
+    from bench import device_synth_tiles
+    src = device_synth_tiles(n, w, h, b, 0, torch.device("cuda"))
+    cfg = q.config(w, h, b, 0, mode=MODE_FTL)
+    dst, sizes, status = q.encode_batch(cfg, src, n)
+    offsets = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, n)
+    torch.cuda.synchronize()
+    assert not status.any().item() and not st.any().item()
+    assert torch.equal(out.view(-1), src.view(-1))
+    sizes_h = sizes.cpu().numpy()
+    O = oracle()
+    for t in (0, 1, 2047, 4095):
+        tile = synth_tiles(1, w, h, b, np.uint8, t0=t)[0]
+        assert np.array_equal(src[t].cpu().numpy().reshape(h, w, b), tile)  # device generator == host generator
+        want = O.encode(tile)
+        assert sizes_h[t] == len(want)
+        assert dst[t, :sizes_h[t]].cpu().numpy().tobytes() == want
+
+
+def test_batch_decode_reports_bad_streams():
+    torch = torch_mod()
+    tiles = synth_tiles(4, 32, 32, 1, np.uint8)
+    cfg, dst, sizes, status = encode_tiles(tiles)
+    dst_h, sizes_h = dst.cpu().numpy().copy(), sizes.cpu().numpy().copy()
+    dst_h[1, 0] = ord("X")           # bad signature
+    sizes_h[2] += 3                  # trailing garbage
+    dst_h[3, 4] = 63                 # geometry differs from the batch
+    d2, s2 = torch.from_numpy(dst_h).cuda(), torch.from_numpy(sizes_h).cuda()
+    offsets = torch.arange(4, device="cuda", dtype=torch.int64) * d2.stride(0)
+    out, st = q.decode_batch(cfg, d2, offsets, s2, 4)
+    torch.cuda.synchronize()
+    assert st.cpu().numpy().tolist() == [q.TILE_OK, q.TILE_BAD_HEADER, q.TILE_CORRUPT, q.TILE_BAD_HEADER]
+    assert np.array_equal(out[0].cpu().numpy().reshape(32, 32, 1), tiles[0])

@@ -108,7 +108,6 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     if (!geometry_ok(cfg) || cfg->mode > M_FTL || cfg->quanta < 1 || !d_src || !d_dst || !d_sizes) return QB3CU_ERR_PARAM;
     if (ntiles == 0) return QB3CU_OK;
     if (ntiles > 0x7fffffffull) return QB3CU_ERR_PARAM;
-    if (cfg->mode != 0 && cfg->mode != 4 && cfg->mode != 8) return QB3CU_ERR_PARAM; /* TODO(best, rle): not on the device yet */
     const uint32_t tsize = TYPESIZE[cfg->dtype], bits = 8 * tsize;
     for (uint32_t c = 0; c < cfg->bands; c++) if (cfg->cband[c] >= cfg->bands) return QB3CU_ERR_PARAM;
     if (((uintptr_t)d_src | src_tile_pitch) % tsize) return QB3CU_ERR_PARAM;
@@ -162,12 +161,15 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     if (threads > 512) return QB3CU_ERR_PARAM;
     a.rowpitch = ((a.seg_blocks * 4 * a.bands * tsize + 15) & ~15u) + 16;
     a.win_words = ((a.hdr_len * 8 + 128 + threads * max_group_bits(bits)) / 32 + 16 + 3) & ~3u;
-    const size_t smem = (size_t)a.win_words * 4 + 4 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4
-                      + 2 * (size_t)a.bands + threads;
+    size_t smem = (size_t)a.win_words * 4 + 4 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4
+                + 2 * (size_t)a.bands + threads;
+    smem = (smem + 7) & ~(size_t)7;
+    a.best_off = (uint32_t)smem;
+    if (a.mode == M_CF_Z || a.mode == M_CF_H) smem += (size_t)threads * 8 + 2 * (size_t)a.bands * 8 + (size_t)threads * 4;
     if (smem > 200 * 1024) return QB3CU_ERR_PARAM;
 
     cudaError_t err = launch_encode(a, tsize, ntiles, threads, smem, static_cast<cudaStream_t>(stream));
-    if (err == cudaSuccess) count_launches(1);
+    if (err == cudaSuccess) count_launches(a.rle_mode ? 2 : 1);
     return note_cuda(err);
 }
 

@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(32) parse_kernel(const DecArgs a)
                     }
                     else {
                         W tbl[8];
-                        uint32_t maxidx = 0, used = 0, idx = 0;
+                        uint32_t maxidx = 0, used = 0;
+                        uint64_t idx = 0;
                         cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
                         rung = (runbits[c * 32 + lane] + cs) & UMASK;
                         runbits[c * 32 + lane] = (uint8_t)rung;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(32) parse_kernel(const DecArgs a)
                             const uint32_t j = (uint32_t)decode_bits(s.peek(), 0, 2, l); /* no swap, reference: QB3decode.h:697 */
                             s.advance(l);
                             used += l;
-                            idx |= j << (3 * i);
+                            idx |= (uint64_t)j << (3 * i);
                             maxidx = max(maxidx, j);
                         }
                         failed |= used > 52;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(32) parse_kernel(const DecArgs a)
                         }
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            const uint32_t j = (idx >> (3 * i)) & 7;
+                            const uint32_t j = (uint32_t)(idx >> (3 * i)) & 7;
                             W v = 0;
 #pragma unroll
                             for (int k = 0; k < 8; k++) if (k == (int)j) v = tbl[k];

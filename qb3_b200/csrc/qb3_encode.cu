@@ -197,12 +197,136 @@ template <typename W> __device__ __forceinline__ void prepare_group(W (&m)[16], 
     }
 }
 
+
+/* ------------------------------------------------------------------ BEST mode helpers */
+
+/* gcd of the non-zero magnitudes of a group, 1 as soon as it is known (reference: gcf, QB3encode.h:98-126) */
+template <typename W> __device__ __forceinline__ W group_gcd(const W (&m)[16])
+{
+    W g = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        W a = magsabs(m[i]);
+        if (g != 1)
+            while (a) { const W t = g % a; g = a; a = t; }
+    }
+    return g;
+}
+
+/* value i of a group as it is coded: step-down flip of value k, then the middle swap */
+template <typename W> __device__ __forceinline__ W coded_value(W v, int i, int k, uint32_t rung)
+{
+    if (i == k) v ^= (W)1 << rung;
+    return group_swaps(rung) ? mswap(v, rung) : v;
+}
+template <typename W> __device__ __forceinline__ int step_index(const W (&m)[16], uint32_t rung)
+{
+    uint32_t M = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) M |= ((uint32_t)(m[i] >> rung) & 1u) << i;
+    return step_encode_index(M);
+}
+/* bits of the 16 values of a group at rung >= 1, with step coding */
+template <typename W> __device__ __forceinline__ uint32_t body_len(const W (&m)[16], uint32_t rung)
+{
+    const int k = step_index(m, rung);
+    uint32_t len = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) len += code_len<W>(coded_value(m[i], i, k, rung), rung);
+    return len;
+}
+/* stand-alone value: qb3csztbl (reference: QB3encode.h:144-150) */
+template <typename W> __device__ __forceinline__ uint32_t single_len(W v, uint32_t rung)
+{
+    if (rung == 0) return 1;
+    return code_len<W>(single_swaps(rung) ? mswap(v, rung) : v, rung);
+}
+/* length of a rung switch written without its change flag; "no change" is spelled as the signal */
+__device__ __forceinline__ uint32_t cs_noflag(uint32_t U, uint32_t delta)
+{
+    uint32_t e = cs_entry(U, delta & ((1u << U) - 1));
+    if ((e >> 12) == 1) e = cs_signal(U);
+    return ((e >> 12) - 1) << 12 | ((e & 0xfff) >> 1);
+}
+
+template <typename W, int BITS> struct ValuePut {
+    __device__ static __forceinline__ void put(Packer &pk, W v, uint32_t rung) /* rung >= 1 */
+    {
+        uint64_t lo; uint32_t hi;
+        const uint32_t l = code_bits<W>(v, rung, lo, hi);
+        if (BITS <= 16) pk.put32((uint32_t)lo, l);
+        else if (BITS == 32 || l <= 64) pk.put64(lo, l);
+        else { pk.put64(lo, 64); pk.put32(hi, 1); } /* 65 bits at rung 63, reference: QB3encode.h:267-275 */
+    }
+    __device__ static __forceinline__ void put_single(Packer &pk, W v, uint32_t rung)
+    {
+        if (rung == 0) { pk.put32((uint32_t)v & 1, 1); return; }
+        put(pk, single_swaps(rung) ? mswap(v, rung) : v, rung);
+    }
+    __device__ static __forceinline__ void put_body(Packer &pk, const W (&m)[16], uint32_t rung)
+    {
+        const int k = step_index(m, rung);
+#pragma unroll
+        for (int i = 0; i < 16; i++) put(pk, coded_value(m[i], i, k, rung), rung);
+    }
+    __device__ static __forceinline__ void put_raw16(Packer &pk, const W (&m)[16]) /* 16 one bit values */
+    {
+        uint32_t b = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) b |= ((uint32_t)m[i] & 1u) << i;
+        pk.put32(b, 16);
+    }
+};
+
+/* Index group analysis (reference: ienc, QB3encode.h:557-613): up to 8 distinct values in first-seen order,
+   stable sorted by descending count; slot[i] = table index of value i. Returns false for more than 8. */
+template <typename W> struct IndexTable {
+    W val[8];
+    uint32_t cnt[8];
+    uint32_t n;
+    uint64_t slots; /* 16 x 3 bits */
+    __device__ bool build(const W (&m)[16])
+    {
+        n = 0;
+        for (int i = 0; i < 16; i++) {
+            uint32_t j = 0;
+            while (j < n && val[j] != m[i]) j++;
+            if (j == n) {
+                if (n == 8) return false;
+                val[n] = m[i]; cnt[n] = 1; n++;
+            }
+            else cnt[j]++;
+        }
+        for (uint32_t i = 1; i < n; i++)
+            for (uint32_t j = i; j > 0 && cnt[j] > cnt[j - 1]; j--) {
+                const W tv = val[j]; val[j] = val[j - 1]; val[j - 1] = tv;
+                const uint32_t tc = cnt[j]; cnt[j] = cnt[j - 1]; cnt[j - 1] = tc;
+            }
+        slots = 0;
+        for (int i = 0; i < 16; i++) {
+            uint32_t j = 0;
+            while (val[j] != m[i]) j++;
+            slots |= (uint64_t)j << (3 * i);
+        }
+        return true;
+    }
+    /* bits after the three prefix fields */
+    __device__ uint32_t payload_len(uint32_t rung) const
+    {
+        uint32_t len = 0;
+        for (int i = 0; i < 16; i++) len += code_len<uint32_t>((uint32_t)(slots >> (3 * i)) & 7, 2);
+        for (uint32_t j = 0; j < n; j++) len += single_len<W>(val[j], rung);
+        return len;
+    }
+};
+
 template <typename T, bool BEST>
 __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ EncArgs a)
 {
     typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
     constexpr uint32_t UMASK = (1u << U) - 1;
+    (void)UMASK;
 
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *win = reinterpret_cast<uint32_t *>(smem);
@@ -211,6 +335,11 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
     uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(carry_prev + 2 * a.bands);                   /* [33] */
     uint8_t *carry_rung = reinterpret_cast<uint8_t *>(scan_scratch + 36);                              /* [2][bands] */
     uint8_t *rung_s = carry_rung + 2 * a.bands;                                                        /* [blockDim] */
+    /* BEST only: the common factor that was last written for each band is the one piece of cross-group state
+       that is not a neighbour lookup; it is propagated with a strided max-scan over the committing groups */
+    unsigned long long *cfm2_s = reinterpret_cast<unsigned long long *>(smem + a.best_off);            /* [blockDim] */
+    unsigned long long *carry_pcf = cfm2_s + blockDim.x;                                               /* [2][bands] */
+    int *commit_s = reinterpret_cast<int *>(carry_pcf + 2 * a.bands);                                  /* [blockDim] */
 
     const uint32_t tid = threadIdx.x, NT = blockDim.x, tile = blockIdx.x;
     const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
@@ -222,6 +351,7 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
         const unsigned long long *st = a.state ? a.state + (uint64_t)tile * 3 * a.bands : nullptr;
         carry_prev[c] = st ? st[c] : 0ull;
         carry_rung[c] = st ? (uint8_t)st[a.bands + c] : (uint8_t)0;
+        if (BEST) carry_pcf[c] = st ? st[2 * a.bands + c] : 0ull;
     }
     for (uint32_t i = tid; i < a.win_words; i += NT) win[i] = 0;
     __syncthreads();
@@ -285,16 +415,95 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
             }
             __syncthreads();
 
-            uint32_t len = 0, cs = 0;
+            uint32_t len = 0, cs = 0, oldrung = 0;
+            /* BEST: 0 plain, 1 common factor, 2 index, 3 nothing (the reference's empty index group, see below) */
+            uint32_t kind = 0, trung = 0, cfrung = 0;
+            bool same = false;
+            W q[16]; /* common factor quotients, BEST only */
+            W cf = 1, cm2 = 0;
             if (active) {
-                const uint32_t oldrung = blk > 0 ? rung_s[tid - a.bands] : carry_rung[par * a.bands + c];
+                oldrung = blk > 0 ? rung_s[tid - a.bands] : carry_rung[par * a.bands + c];
                 cs = switch_entry<U>(rung, oldrung);
-                len = cs >> 12;
-                if (bitsused <= 1) len += 1 + (bitsused ? 16 : 0); /* reference: QB3encode.h:159-166 */
-                else {
-                    prepare_group<W>(m, rung, use_step);
+            }
+            if (!BEST) {
+                if (active) {
+                    len = cs >> 12;
+                    if (bitsused <= 1) len += 1 + (bitsused ? 16 : 0); /* reference: QB3encode.h:159-166 */
+                    else {
+                        prepare_group<W>(m, rung, use_step);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) len += code_len<W>(m[i], rung);
+                        for (int i = 0; i < 16; i++) len += code_len<W>(m[i], rung);
+                    }
+                }
+            }
+            else {
+                /* reference: encode_best, QB3encode.h:691-713 */
+                const W TM = (W)lowmask64(BITS);
+                uint32_t l_plain = 0, l_same = 0, l_diff = 0, l_idx = 800;
+                bool idx_elig = false, commit = false;
+                const uint32_t idx_min = 36 + 3 * U;
+                if (active) {
+                    len = cs >> 12;
+                    if (bitsused <= 1) len += 1 + (bitsused ? 16 : 0);
+                    else {
+                        cf = group_gcd<W>(m);
+                        if (cf >= 2) { /* reference: cfgenc, QB3encode.h:283-361 */
+                            W qbits = 0;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) qbits |= q[i] = (((magsabs(m[i]) / cf) << 1) - (m[i] & 1)) & TM;
+                            cm2 = (cf - 2) & TM;
+                            trung = topbit((W)(qbits | 1));
+                            cfrung = topbit((W)(cm2 | 1));
+                            const uint32_t body = trung == 0 ? 16 : body_len<W>(q, trung);
+                            l_same = (U + 2) + (cs_noflag(U, trung - oldrung) >> 12) + 1 + body;
+                            uint32_t cfl;
+                            if (trung >= cfrung && (trung < cfrung + U || cfrung == 0))
+                                cfl = 1 + (trung == 0 ? 1 : single_len<W>(cm2, trung));
+                            else
+                                cfl = (cs_entry(U, (cfrung - trung) & UMASK) >> 12) + single_len<W>(cm2 ^ ((W)1 << cfrung), cfrung - 1);
+                            l_diff = l_same + cfl;
+                        }
+                        else l_plain = (cs >> 12) + body_len<W>(m, rung);
+                        idx_elig = rung > 3 && rung < 63;
+                        if (idx_elig) {
+                            IndexTable<W> tb;
+                            if (tb.build(m))
+                                l_idx = (U + 2) + (cs_noflag(U, UMASK - oldrung) >> 12) + (cs_noflag(U, rung - oldrung) >> 12)
+                                      + tb.payload_len(rung);
+                        }
+                        const uint32_t sz = cf >= 2 ? l_diff : l_plain;
+                        commit = cf >= 2 && !(idx_elig && sz >= idx_min + 2 * rung && l_idx < sz);
+                    }
+                }
+                /* previous common factor of this band: the latest earlier group of the band that committed one.
+                   Inclusive max-scan of the committing thread index with stride 'bands', in shared memory. */
+                int last = (active && commit) ? (int)tid : -1;
+                cfm2_s[tid] = (unsigned long long)cm2;
+                for (uint32_t d = a.bands; d < ng; d <<= 1) {
+                    commit_s[tid] = last;
+                    __syncthreads();
+                    if (tid >= d && tid < ng) last = max(last, commit_s[tid - d]);
+                    __syncthreads();
+                }
+                commit_s[tid] = last;
+                __syncthreads();
+                if (active) {
+                    const int before = blk > 0 ? commit_s[tid - a.bands] : -1;
+                    const W pcf = (W)(before >= 0 ? cfm2_s[before] : carry_pcf[par * a.bands + c]);
+                    if (blk == nblk - 1)
+                        carry_pcf[(par ^ 1) * a.bands + c] = last >= 0 ? cfm2_s[last] : carry_pcf[par * a.bands + c];
+                    if (bitsused > 1) {
+                        same = cf >= 2 && pcf == cm2;
+                        const uint32_t sz = cf >= 2 ? (same ? l_same : l_diff) : l_plain;
+                        kind = cf >= 2 ? 1 : 0;
+                        len = sz;
+                        if (idx_elig && sz >= idx_min + 2 * rung && l_idx < sz) {
+                            /* more than 8 distinct values report 800 bits; when the group is longer than that (64 bit
+                               data only) the reference replaces it by the empty side buffer (QB3encode.h:704-708) */
+                            kind = l_idx == 800 ? 3 : 2;
+                            len = l_idx == 800 ? 0 : l_idx;
+                        }
+                    }
                 }
             }
             uint32_t total;
@@ -303,7 +512,55 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
             const uint32_t s = wbits + off, e = s + len;
             Packer pk;
             pk.start(win, s);
-            if (active) {
+            if (BEST && active && kind != 0) {
+                typedef ValuePut<W, BITS> VP;
+                const uint32_t sig = cs_signal(U);
+                if (kind == 1) { /* common factor group */
+                    uint32_t e = cs_noflag(U, trung - oldrung);
+                    pk.put32(sig & 0xfff, sig >> 12);
+                    pk.put32(e & 0xfff, e >> 12);
+                    bool done = false;
+                    if (!same) {
+                        pk.put32(1, 1);
+                        if (trung >= cfrung && (trung < cfrung + U || cfrung == 0)) {
+                            pk.put32(0, 1);
+                            if (trung == 0) { pk.put32((uint32_t)cm2 & 1, 1); VP::put_raw16(pk, q); done = true; }
+                            else VP::put_single(pk, cm2, trung);
+                        }
+                        else {
+                            e = cs_entry(U, (cfrung - trung) & UMASK);
+                            pk.put32(e & 0xfff, e >> 12);
+                            VP::put_single(pk, cm2 ^ ((W)1 << cfrung), cfrung - 1);
+                            if (trung == 0) { VP::put_raw16(pk, q); done = true; }
+                        }
+                    }
+                    else {
+                        pk.put32(0, 1);
+                        if (trung == 0) { VP::put_raw16(pk, q); done = true; }
+                    }
+                    if (!done) VP::put_body(pk, q, trung);
+                }
+                else if (kind == 2) { /* index group */
+                    IndexTable<W> tb;
+                    tb.build(m);
+                    uint32_t e = cs_noflag(U, UMASK - oldrung);
+                    pk.put32(sig & 0xfff, sig >> 12);
+                    pk.put32(e & 0xfff, e >> 12);
+                    e = cs_noflag(U, rung - oldrung);
+                    pk.put32(e & 0xfff, e >> 12);
+                    for (int i = 0; i < 16; i++) {
+                        uint64_t lo; uint32_t hi;
+                        const uint32_t l = code_bits<uint32_t>((uint32_t)(tb.slots >> (3 * i)) & 7, 2, lo, hi);
+                        pk.put32((uint32_t)lo, l); /* no middle swap, reference: QB3encode.h:599-601 */
+                    }
+                    for (uint32_t j = 0; j < tb.n; j++) VP::put_single(pk, tb.val[j], rung);
+                }
+            }
+            else if (BEST && active && bitsused > 1) { /* plain group, always with step coding */
+                pk.put32(cs & 0xfff, cs >> 12);
+                ValuePut<W, BITS>::put_body(pk, m, rung);
+            }
+            else if (active) {
                 pk.put32(cs & 0xfff, cs >> 12);
                 if (bitsused <= 1) {
                     uint32_t b = (uint32_t)bitsused;
@@ -352,6 +609,7 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
         for (uint32_t c = tid; c < a.bands; c += NT) {
             st[c] = carry_prev[(it & 1) * a.bands + c];
             st[a.bands + c] = carry_rung[(it & 1) * a.bands + c];
+            if (BEST) st[2 * a.bands + c] = carry_pcf[(it & 1) * a.bands + c];
         }
     }
 
@@ -361,7 +619,8 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
         st_stream16(dst + flushed * 16, reinterpret_cast<const uint4 *>(win)[0]);
 
     /* stored fallback when coding did not shrink the tile (reference: QB3encode.cpp:570-573, 461-485) */
-    if (a.small == 3 || overflow || a.raw_size <= len_bytes) {
+    /* with an RLE mode the choice is left to rle_kernel: the reference tries RLE first (QB3encode.cpp:536-573) */
+    if (a.small == 3 || overflow || (!a.rle_mode && a.raw_size <= len_bytes)) {
         __syncthreads();
         for (uint32_t i = tid; i < a.hdr_stored_len; i += NT) dst[i] = a.hdr_stored[i];
         const uint64_t line = (uint64_t)a.w * a.bands * sizeof(T), pitch = a.stride * sizeof(T);
@@ -377,6 +636,110 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
     }
 }
 
+
+/* ------------------------------------------------------------------ RLE0 byte pass */
+
+/*
+ * RLE0 / RLE0Size (reference: QB3encode.cpp:271-332) by one warp: "FF FF" becomes "FF FF FF", four or more zero
+ * bytes become "FF FF n" (n = count - 4, at most 0xfe) unless the byte emitted just before was a literal FF; the
+ * last two bytes are always literal. The scanner is serial by nature, but between candidate positions (an equal
+ * pair of 00 or FF) it moves one literal byte at a time, so a warp looks at 32 positions per step, copies the
+ * literals in front of the first candidate together and only resolves candidates one by one.
+ * out == nullptr only measures. Returns the output size (warp uniform).
+ */
+__device__ static uint64_t rle_pass(const uint8_t *p, uint64_t n, uint8_t *out)
+{
+    const uint32_t FULL = 0xffffffffu, lane = lane_id();
+    const uint64_t lim = n >= 2 ? n - 2 : 0; /* a pair or run cannot start in the last two bytes */
+    uint64_t i = 0, o = 0;
+    uint32_t last = 0;
+    while (i < lim) {
+        const uint64_t pos = i + lane;
+        const uint32_t b = pos < n ? p[pos] : 1u;
+        uint32_t nb = __shfl_down_sync(FULL, b, 1);
+        if (lane == 31) nb = pos + 1 < n ? p[pos + 1] : 1u;
+        const bool cand = pos < lim && b == nb && (b == 0 || b == 0xff);
+        const uint32_t mask = __ballot_sync(FULL, cand);
+        const uint32_t k = mask ? (uint32_t)__ffs((int)mask) - 1 : 32;
+        const uint32_t nlit = (uint32_t)min((uint64_t)k, lim - i);
+        if (nlit) {
+            if (out && lane < nlit) out[o + lane] = (uint8_t)b;
+            last = __shfl_sync(FULL, b, nlit - 1);
+            o += nlit;
+            i += nlit;
+        }
+        if (k == 32) continue;
+        const uint32_t c = __shfl_sync(FULL, b, k); /* the candidate, now at position i */
+        if (c == 0xff) {
+            if (out && lane < 3) out[o + lane] = 0xff;
+            o += 3; i += 2; last = 0;
+            continue;
+        }
+        const bool run = last != 0xff && n - (i + 1) >= 3 && p[i + 2] == 0 && p[i + 3] == 0;
+        if (!run) {
+            if (out && lane == 0) out[o] = 0;
+            o += 1; i += 1; last = 0;
+            continue;
+        }
+        i += 4;
+        uint32_t r = 0; /* zeros beyond the first four */
+        for (;;) {
+            const uint64_t q = i + r + lane;
+            const bool z = q < n && r + lane < 0xfe && p[q] == 0;
+            const uint32_t zm = __ballot_sync(FULL, z);
+            const uint32_t here = zm == FULL ? 32 : (uint32_t)__ffs((int)~zm) - 1;
+            r += here;
+            if (here < 32) break;
+        }
+        if (out && lane < 3) out[o + lane] = lane < 2 ? 0xff : (uint8_t)r;
+        o += 3; i += r; last = 0;
+    }
+    while (i < n) {
+        const uint64_t pos = i + lane;
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, n - i);
+        if (out && pos < n) out[o + lane] = p[pos];
+        o += cnt; i += cnt;
+    }
+    return o;
+}
+
+/* One warp per tile, after encode_kernel, for the RLE modes only: RLE when it pays, else the stored check
+   (reference: QB3encode.cpp:536-573). */
+__global__ void __launch_bounds__(128) rle_kernel(const __grid_constant__ EncArgs a, uint32_t ntiles)
+{
+    const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (tile >= ntiles) return;
+    uint8_t *dst = a.dst + (uint64_t)tile * a.slot;
+    const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
+    if (dst[10] == M_STORED) return; /* already final */
+    const uint64_t len = a.sizes[tile], hdr = a.hdr_len, data = len - hdr;
+    if (len <= a.max_size / 2) { /* "a vague limit", but it decides the bytes */
+        const uint64_t avail = a.max_size - len;
+        const uint64_t rsz = rle_pass(dst + hdr, data, nullptr);
+        if (rsz <= avail && rsz < data) {
+            rle_pass(dst + hdr, data, dst + len); /* into the free tail of the slot, then down over the data */
+            __syncwarp();
+            for (uint64_t k = lane; k < rsz; k += 32) dst[hdr + k] = dst[len + k];
+            if (lane == 0) {
+                dst[10] = (uint8_t)a.rle_mode;
+                a.sizes[tile] = hdr + rsz;
+            }
+            return;
+        }
+    }
+    if (a.raw_size <= len) { /* stored fallback, reference: QB3encode.cpp:461-485 */
+        const uint32_t ts = a.raw_size / ((uint64_t)a.w * a.h * a.bands);
+        const uint64_t line = (uint64_t)a.w * a.bands * ts, pitch = a.stride * ts;
+        __syncwarp();
+        for (uint32_t i = lane; i < a.hdr_stored_len; i += 32) dst[i] = a.hdr_stored[i];
+        for (uint64_t i = lane; i < a.raw_size; i += 32) {
+            const uint64_t y = i / line, x = i - y * line;
+            dst[a.hdr_stored_len + i] = src[y * pitch + x];
+        }
+        if (lane == 0) a.sizes[tile] = a.hdr_stored_len + a.raw_size;
+    }
+}
+
 /* ------------------------------------------------------------------ launch */
 
 template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st)
@@ -386,6 +749,9 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<(unsigned)ntiles, threads, smem, st>>>(a);
+    err = cudaGetLastError();
+    if (err != cudaSuccess || !a.rle_mode) return err;
+    rle_kernel<<<(unsigned)((ntiles + 3) / 4), 128, 0, st>>>(a, (uint32_t)ntiles);
     return cudaGetLastError();
 }
 

@@ -173,10 +173,64 @@ __device__ static uint64_t derle_size(const uint8_t *p, uint64_t len)
     return n + (len - i);
 }
 
+
+/*
+ * Register bit buffer for the fast path (8 and 16 bit types, no RLE): 64 bits of look-ahead fed by aligned 32 bit
+ * loads with one word of read-ahead, so the load latency stays off the parse chain. After refill() at least 33 bits
+ * are valid, which covers every field of these types (a code is at most 17 bits). Zero fill past the end.
+ */
+struct FastBits {
+    const uint32_t *base;
+    uint64_t buf;
+    uint32_t nwords, k, tailmask, mis8, nb, nxt;
+
+    __device__ __forceinline__ uint32_t load(uint32_t i) const
+    {
+        uint32_t w = i < nwords ? __ldg(base + i) : 0u;
+        if (i + 1 == nwords) w &= tailmask;
+        return w;
+    }
+    __device__ __forceinline__ void open(const uint8_t *p, uint64_t len)
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)p & 3);
+        const uint64_t span = mis + len;
+        const uint32_t tail = (uint32_t)span & 3;
+        base = reinterpret_cast<const uint32_t *>(p - mis);
+        nwords = (uint32_t)((span + 3) >> 2);
+        tailmask = tail ? (1u << (8 * tail)) - 1 : 0xffffffffu;
+        mis8 = 8 * mis;
+        buf = (uint64_t)(load(0) >> mis8);
+        nb = 32 - mis8;
+        buf |= (uint64_t)load(1) << nb;
+        nb += 32;
+        nxt = load(2);
+        k = 3;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (nb <= 32) {
+            buf |= (uint64_t)nxt << nb;
+            nb += 32;
+            nxt = load(k);
+            k++;
+        }
+    }
+    __device__ __forceinline__ uint64_t peek() { refill(); return buf; }
+    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; } /* n <= 33, after peek() / refill() */
+    __device__ __forceinline__ uint64_t get(uint32_t n)
+    {
+        refill();
+        const uint64_t v = buf & lowmask64(n);
+        advance(n);
+        return v;
+    }
+    __device__ __forceinline__ uint64_t consumed() const { return 32ull * (k - 1) - mis8 - nb; }
+};
+
 /* ------------------------------------------------------------------ group parse */
 
 /* 16 values at a rung (reference: QB3decode.h:142-290); use_step undoes the step-down flip (:285-289) */
-template <typename W> __device__ __forceinline__ void read_group(Reader &s, uint32_t rung, W (&g)[16], bool use_step)
+template <typename W, typename S> __device__ __forceinline__ void read_group(S &s, uint32_t rung, W (&g)[16], bool use_step)
 {
     if (rung == 0) {
         uint32_t b = 0;
@@ -191,7 +245,7 @@ template <typename W> __device__ __forceinline__ void read_group(Reader &s, uint
         const uint64_t x = s.peek();
         uint32_t len, x64 = 0;
         if (sizeof(W) == 8 && rung == 63 && (x & 3) == 3) { /* 65 bit code, reference: QB3decode.h:272-282 */
-            Reader t = s;
+            S t = s;
             t.advance(64);
             x64 = (uint32_t)t.peek() & 1;
         }
@@ -209,7 +263,7 @@ template <typename W> __device__ __forceinline__ void read_group(Reader &s, uint
 }
 
 /* stand-alone value (reference: qb3dsztbl, QB3decode.h:132-138) */
-__device__ __forceinline__ uint64_t read_single(Reader &s, uint32_t rung)
+template <typename S> __device__ __forceinline__ uint64_t read_single(S &s, uint32_t rung)
 {
     if (rung == 0) return s.get(1);
     uint32_t len;
@@ -219,8 +273,226 @@ __device__ __forceinline__ uint64_t read_single(Reader &s, uint32_t rung)
     return v;
 }
 
+
+/*
+ * The group that follows a SIGNAL: a common factor group or an index group (reference: QB3decode.h:624-716).
+ * rb is the band's running rung, pcf its last common factor; both are updated. Returns true on the reference's
+ * failure conditions (QB3decode.h:642,665,683,703).
+ */
+template <typename W, int BITS, int U, typename S>
+__device__ __noinline__ bool read_special_group(S &s, W (&g)[16], uint8_t &rb, W &pcf)
+{
+    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
+    const W TM = (W)lowmask64(BITS);
+    bool failed = false;
+    uint32_t cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
+    uint32_t rung = (rb + cs) & UMASK;
+    s.advance((cs >> 12) - 1);
+    if (rung != UMASK) { /* common factor */
+        uint32_t cfrung = rung;
+        W cf = pcf;
+        if (s.get(1)) {
+            const uint32_t own = (uint32_t)s.get(1);
+            if (own) {
+                cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
+                cfrung = (rung + cs) & UMASK;
+                failed |= cfrung == rung;
+                s.advance((cs >> 12) - 1);
+            }
+            if (own && cfrung == 0) return true; /* the reference indexes a table at -1 here */
+            cf = (W)(read_single(s, cfrung - own) + ((uint64_t)own << cfrung)) & TM;
+            pcf = cf;
+        }
+        cf = (cf + 2) & TM;
+        if (rung) {
+            W used = 0;
+            read_group<W>(s, rung, g, true);
+#pragma unroll
+            for (int i = 0; i < 16; i++) /* magsmul, reference: QB3decode.h:575 */
+                used |= g[i] = (magsabs(g[i]) * (W)(cf << 1) - (g[i] & 1)) & TM;
+            rb = (uint8_t)topbit((W)(used | 1));
+            failed |= cf > used;
+        }
+        else {
+            const W v = (((cf - 1) << 1) | 1) & TM;
+            const uint32_t b = (uint32_t)s.get(16);
+#pragma unroll
+            for (int i = 0; i < 16; i++) g[i] = ((b >> i) & 1) ? v : (W)0;
+            rb = (uint8_t)topbit((W)(v | 1));
+        }
+        return failed;
+    }
+    /* index group */
+    W tbl[8];
+    uint32_t maxidx = 0, used = 0;
+    uint64_t idx = 0;
+    cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
+    rung = (rb + cs) & UMASK;
+    rb = (uint8_t)rung;
+    failed |= rung == 63;
+    s.advance((cs >> 12) - 1);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t l;
+        const uint32_t j = (uint32_t)decode_bits(s.peek(), 0, 2, l); /* no swap, reference: QB3decode.h:697 */
+        s.advance(l);
+        used += l;
+        idx |= (uint64_t)j << (3 * i);
+        maxidx = max(maxidx, j);
+    }
+    failed |= used > 52;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tbl[i] = 0;
+    for (uint32_t i = 0; i <= maxidx; i++) {
+        const W v = (W)read_single(s, rung);
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k == (int)i) tbl[k] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t j = (uint32_t)(idx >> (3 * i)) & 7;
+        W v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k == (int)j) v = tbl[k];
+        g[i] = v;
+    }
+    return failed;
+}
+
+/*
+ * Fast path: 8 and 16 bit types, no RLE, regular geometry. Same parse as the general path, but
+ *  - bits come from the register buffer above, values are decoded with rung-uniform 32 bit arithmetic
+ *    (no tables, no rung branches inside the 16 value loop)
+ *  - pixels are not scattered to global memory one by one: each lane owns four staged rows of a few blocks
+ *    in shared memory (odd word stride between lanes, so no bank conflicts) and writes them out as whole
+ *    words when the staging group is full. Groups wider than the staging budget are written directly.
+ */
+template <typename T, bool STAGED>
+__device__ bool decode_fast(const DecArgs &a, const StreamInfo &info, const uint8_t *payload, uint64_t plen, T *out,
+                            uint32_t *prev, uint32_t *pcf, uint8_t *runbits, uint8_t *stage, uint32_t lane_stride,
+                            uint32_t stage_blocks)
+{
+    typedef uint32_t W;
+    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
+    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
+    constexpr W TM = (W)((1ull << BITS) - 1);
+    const uint32_t lane = threadIdx.x;
+    const uint64_t order = info.order ? info.order : HILBERT;
+    const bool ftl = info.mode == M_FTL;
+    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, bands = a.bands;
+
+    FastBits s;
+    s.open(payload, plen);
+
+    /* element offsets of the 16 curve positions inside the destination of a block */
+    const uint32_t rowelems = STAGED ? stage_blocks * 4 * bands : (uint32_t)a.stride;
+    uint32_t off[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t n = (uint32_t)(order >> (4 * (15 - i))) & 15;
+        off[i] = (n >> 2) * rowelems + (n & 3) * bands;
+    }
+    T *const lane_stage = reinterpret_cast<T *>(stage + (size_t)lane * lane_stride);
+    for (uint32_t c = 0; c < bands; c++) { prev[c * 32 + lane] = 0; pcf[c * 32 + lane] = 0; runbits[c * 32 + lane] = 0; }
+
+    bool failed = false;
+    for (uint32_t by = 0; by < nby && !failed; by++) {
+        const uint32_t y0 = min(4 * by, a.h - 4);
+        for (uint32_t gb = 0; gb < nbx && !failed; gb += stage_blocks) {
+            const uint32_t gend = min(nbx, gb + stage_blocks);
+            const uint32_t xs = min(4 * gb, a.w - 4), xe = min(4 * gend, a.w);
+            for (uint32_t bx = gb; bx < gend && !failed; bx++) {
+                const uint32_t x0 = min(4 * bx, a.w - 4);
+                for (uint32_t c = 0; c < bands; c++) {
+                    W g[16];
+                    uint32_t cs = 0;
+                    s.refill();
+                    if (s.buf & 1) {
+                        cs = ds_entry(U, (uint32_t)(s.buf >> 1) & LMASK);
+                        s.advance(cs >> 12);
+                    }
+                    else s.advance(1);
+                    if (ftl || (cs & 0xfff) != 0 || cs == 0) {
+                        const uint32_t r = (runbits[c * 32 + lane] + cs) & UMASK;
+                        runbits[c * 32 + lane] = (uint8_t)r;
+                        if (r == 0) { /* flag, then 16 raw bits (reference: QB3decode.h:148-160) */
+                            s.refill();
+                            const uint32_t x = (uint32_t)s.buf;
+                            const uint32_t b = (x & 1) ? (x >> 1) & 0xffffu : 0u;
+                            s.advance((x & 1) ? 17 : 1);
+#pragma unroll
+                            for (int i = 0; i < 16; i++) g[i] = (b >> i) & 1;
+                        }
+                        else {
+                            const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
+                            uint32_t M = 0;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                s.refill();
+                                const uint32_t x = (uint32_t)s.buf;
+                                const uint32_t b0 = x & 1, t = b0 & (x >> 1);
+                                const uint32_t ht = half << t;
+                                uint32_t v = ((x >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
+                                s.advance(r + b0 + t);
+                                if (v - fm1 <= 1u) v ^= sm; /* middle swap at rungs 1..7 */
+                                g[i] = v;
+                                M |= ((v >> r) & 1u) << i;
+                            }
+                            if (!ftl) {
+                                const int k = step_decode_index(M);
+#pragma unroll
+                                for (int i = 0; i < 16; i++) if (i == k) g[i] ^= 1u << r;
+                            }
+                        }
+                    }
+                    else { /* rare: keep the by-reference array of the out-of-line call away from the hot registers */
+                        W sg[16];
+                        if (read_special_group<W, BITS, U>(s, sg, runbits[c * 32 + lane], pcf[c * 32 + lane])) { failed = true; break; }
+#pragma unroll
+                        for (int i = 0; i < 16; i++) g[i] = sg[i];
+                    }
+
+                    W prv = prev[c * 32 + lane];
+                    T *dstp = STAGED ? lane_stage + (size_t)(x0 - xs) * bands + c
+                                     : out + (uint64_t)y0 * a.stride + (uint64_t)x0 * bands + c;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        prv = (prv + smag<BITS, W>(g[i])) & TM;
+                        dstp[off[i]] = (T)prv;
+                    }
+                    prev[c * 32 + lane] = prv;
+                }
+            }
+            if (STAGED && !failed) { /* staged rows leave as whole words when the destination allows */
+                const uint32_t rowbytes = (xe - xs) * bands * (uint32_t)sizeof(T), srow = rowelems * (uint32_t)sizeof(T);
+                for (uint32_t r = 0; r < 4; r++) {
+                    uint8_t *gp = reinterpret_cast<uint8_t *>(out + (uint64_t)(y0 + r) * a.stride + (uint64_t)xs * bands);
+                    const uint8_t *sp = reinterpret_cast<const uint8_t *>(lane_stage) + r * srow;
+                    if ((((uintptr_t)gp | rowbytes) & 15) == 0) {
+                        for (uint32_t j = 0; j < rowbytes; j += 16) {
+                            const uint32_t *w = reinterpret_cast<const uint32_t *>(sp + j);
+                            *reinterpret_cast<uint4 *>(gp + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                    else if ((((uintptr_t)gp | rowbytes) & 3) == 0) {
+                        for (uint32_t j = 0; j < rowbytes; j += 4)
+                            *reinterpret_cast<uint32_t *>(gp + j) = *reinterpret_cast<const uint32_t *>(sp + j);
+                    }
+                    else {
+                        for (uint32_t j = 0; j < rowbytes; j += sizeof(T))
+                            *reinterpret_cast<T *>(gp + j) = *reinterpret_cast<const T *>(sp + j);
+                    }
+                }
+            }
+        }
+    }
+    if (failed) return true;
+    const uint64_t total = 8 * plen, used = s.consumed();
+    return total > used && total - used > 7; /* reference: QB3decode.h:411,740 */
+}
+
 template <typename T>
-__global__ void __launch_bounds__(32) parse_kernel(const DecArgs a)
+__global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, uint32_t stage_off, uint32_t lane_stride, uint32_t stage_blocks)
 {
     typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -259,6 +531,14 @@ __global__ void __launch_bounds__(32) parse_kernel(const DecArgs a)
         logical = derle_size(payload, plen);
         if (logical > raw) { a.status[tile] = QB3CU_TILE_RLE_TOO_BIG; return; } /* reference: QB3decode.cpp:401 */
     }
+    if (sizeof(T) <= 2 && !rle && a.w >= 4 && a.h >= 4) {
+        uint32_t *p32 = reinterpret_cast<uint32_t *>(prev), *c32 = reinterpret_cast<uint32_t *>(pcf);
+        const bool bad = stage_blocks
+            ? decode_fast<T, true>(a, info, payload, plen, out, p32, c32, runbits, smem + stage_off, lane_stride, stage_blocks)
+            : decode_fast<T, false>(a, info, payload, plen, out, p32, c32, runbits, nullptr, 0, 1);
+        a.status[tile] = bad ? QB3CU_TILE_CORRUPT : QB3CU_TILE_OK;
+        return;
+    }
     Reader s;
     s.open(payload, plen, rle, logical);
 
@@ -291,78 +571,11 @@ __global__ void __launch_bounds__(32) parse_kernel(const DecArgs a)
                     runbits[c * 32 + lane] = (uint8_t)rung;
                     read_group<W>(s, rung, g, !ftl);
                 }
-                else { /* signal: common factor or index group, reference: QB3decode.h:624-716 */
-                    cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
-                    uint32_t rung = (runbits[c * 32 + lane] + cs) & UMASK;
-                    s.advance((cs >> 12) - 1);
-                    if (rung != UMASK) {
-                        uint32_t cfrung = rung;
-                        W cf = pcf[c * 32 + lane];
-                        if (s.get(1)) {
-                            const uint32_t own = (uint32_t)s.get(1);
-                            if (own) {
-                                cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
-                                cfrung = (rung + cs) & UMASK;
-                                failed |= cfrung == rung;
-                                s.advance((cs >> 12) - 1);
-                            }
-                            if (own && cfrung == 0) { failed = true; break; }
-                            cf = (W)(read_single(s, cfrung - own) + ((uint64_t)own << cfrung)) & TM;
-                            pcf[c * 32 + lane] = cf;
-                        }
-                        cf = (cf + 2) & TM;
-                        if (rung) {
-                            W used = 0;
-                            read_group<W>(s, rung, g, true);
+                else { /* signal: common factor or index group */
+                    W sg[16];
+                    if (read_special_group<W, BITS, U>(s, sg, runbits[c * 32 + lane], pcf[c * 32 + lane])) { failed = true; break; }
 #pragma unroll
-                            for (int i = 0; i < 16; i++) /* magsmul, reference: QB3decode.h:575 */
-                                used |= g[i] = (magsabs(g[i]) * (W)(cf << 1) - (g[i] & 1)) & TM;
-                            runbits[c * 32 + lane] = (uint8_t)topbit((W)(used | 1));
-                            failed |= cf > used;
-                        }
-                        else {
-                            const W v = (((cf - 1) << 1) | 1) & TM;
-                            const uint32_t b = (uint32_t)s.get(16);
-#pragma unroll
-                            for (int i = 0; i < 16; i++) g[i] = ((b >> i) & 1) ? v : (W)0;
-                            runbits[c * 32 + lane] = (uint8_t)topbit((W)(v | 1));
-                        }
-                    }
-                    else {
-                        W tbl[8];
-                        uint32_t maxidx = 0, used = 0;
-                        uint64_t idx = 0;
-                        cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
-                        rung = (runbits[c * 32 + lane] + cs) & UMASK;
-                        runbits[c * 32 + lane] = (uint8_t)rung;
-                        failed |= rung == 63;
-                        s.advance((cs >> 12) - 1);
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            uint32_t l;
-                            const uint32_t j = (uint32_t)decode_bits(s.peek(), 0, 2, l); /* no swap, reference: QB3decode.h:697 */
-                            s.advance(l);
-                            used += l;
-                            idx |= (uint64_t)j << (3 * i);
-                            maxidx = max(maxidx, j);
-                        }
-                        failed |= used > 52;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) tbl[i] = 0;
-                        for (uint32_t i = 0; i <= maxidx; i++) {
-                            const W v = (W)read_single(s, rung);
-#pragma unroll
-                            for (int k = 0; k < 8; k++) if (k == (int)i) tbl[k] = v;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            const uint32_t j = (uint32_t)(idx >> (3 * i)) & 7;
-                            W v = 0;
-#pragma unroll
-                            for (int k = 0; k < 8; k++) if (k == (int)j) v = tbl[k];
-                            g[i] = v;
-                        }
-                    }
+                    for (int i = 0; i < 16; i++) g[i] = sg[i];
                 }
                 /* undo the running delta and scatter (reference: QB3decode.h:717-722) */
                 W prv = prev[c * 32 + lane];
@@ -453,10 +666,20 @@ __global__ void __launch_bounds__(256) finish_kernel(const DecArgs a, uint32_t r
 template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaStream_t st)
 {
     typedef typename traits<T>::W W;
-    const size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
+    size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
+    /* fast path staging: as many blocks per lane as fit 192 bytes per staged row, none when one block is wider */
+    uint32_t stage_blocks = 0, lane_stride = 0, stage_off = 0;
+    const uint32_t block_row_bytes = 4 * a.bands * (uint32_t)sizeof(T);
+    if (sizeof(T) <= 2 && block_row_bytes <= 192) {
+        stage_blocks = 192 / block_row_bytes;
+        lane_stride = 4 * stage_blocks * block_row_bytes;
+        lane_stride = ((lane_stride + 3) & ~3u) | 4; /* an odd number of words: lanes fall on different banks */
+        stage_off = (uint32_t)((smem + 15) & ~(size_t)15);
+        smem = stage_off + (size_t)32 * lane_stride;
+    }
     cudaError_t err = cudaFuncSetAttribute(parse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    parse_kernel<T><<<(a.ntiles + 31) / 32, 32, smem, st>>>(a);
+    parse_kernel<T><<<(a.ntiles + 31) / 32, 32, smem, st>>>(a, stage_off, lane_stride, stage_blocks);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     const uint32_t rows_per_cta = 16;

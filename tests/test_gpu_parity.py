@@ -78,7 +78,13 @@ def test_api_round_trip_and_oracle_all_content(dt):
                     continue
                 s = P.encode(img, mode=mode)
                 assert s == O.encode(img, mode=mode), (kind, w, h, b, mode)
-                assert np.array_equal(P.decode(s), img), (kind, w, h, b, mode)
+                d, od = P.decode(s), O.decode(s)
+                assert (d is None) == (od is None) and (d is None or np.array_equal(d, od)), (kind, w, h, b, mode)
+                # The reference cannot read back two kinds of its own streams, and neither may we: an RLE stream
+                # that expands past the raw size (tiny images, QB3encode.cpp:543 vs QB3decode.cpp:401) and 64 bit
+                # BEST groups longer than 800 bits, which it drops (QB3encode.h:564,705). Everything else round trips.
+                known_defect = (od is None and s[10] in (2, 3, 6, 7)) or (np.dtype(dt).itemsize == 8 and mode in (1, 5, 7))
+                assert known_defect or np.array_equal(d, img), (kind, w, h, b, mode)
 
 
 def test_api_quanta_stride_state():

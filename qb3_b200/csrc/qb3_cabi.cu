@@ -161,11 +161,14 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     if (threads > 512) return QB3CU_ERR_PARAM;
     a.rowpitch = ((a.seg_blocks * 4 * a.bands * tsize + 15) & ~15u) + 16;
     a.win_words = ((a.hdr_len * 8 + 128 + threads * max_group_bits(bits)) / 32 + 16 + 3) & ~3u;
-    size_t smem = (size_t)a.win_words * 4 + 4 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4
+    size_t smem = (size_t)a.win_words * 4 + 8 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4
                 + 2 * (size_t)a.bands + threads;
     smem = (smem + 7) & ~(size_t)7;
     a.best_off = (uint32_t)smem;
     if (a.mode == M_CF_Z || a.mode == M_CF_H) smem += (size_t)threads * 8 + 2 * (size_t)a.bands * 8 + (size_t)threads * 4;
+    smem = (smem + 7) & ~(size_t)7;
+    a.lut_off = (uint32_t)smem;
+    smem += 508 * 4 + 64 * 2;
     if (smem > 200 * 1024) return QB3CU_ERR_PARAM;
 
     cudaError_t err = launch_encode(a, tsize, ntiles, threads, smem, static_cast<cudaStream_t>(stream));

@@ -42,6 +42,7 @@ struct EncArgs {
     uint32_t rowpitch;    /* bytes between staged rows in shared memory, multiple of 16 */
     uint32_t win_words;   /* bit window size in 32 bit words */
     uint32_t best_off;    /* byte offset of the BEST mode scratch in shared memory, 8 byte aligned */
+    uint32_t lut_off;     /* byte offset of the code tables in shared memory, 8 byte aligned */
     uint32_t hdr_len, hdr_stored_len;
     uint8_t hdr[MAXHDR];        /* headers up to and including "DT", mode byte = mode */
     uint8_t hdr_stored[MAXHDR]; /* same for the stored fallback (mode 255, no CB / SC) */

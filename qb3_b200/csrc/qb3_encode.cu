@@ -60,6 +60,16 @@ template <int BITS> __device__ __forceinline__ uint64_t quantize_value(uint64_t 
  * Fast path: 16 byte copies at the source's own alignment (row r lands at stage + r * rowpitch + (addr & 15)).
  * General path: element by element through the small-image reorder (QB3encode.cpp:351-389) and the quantiser.
  */
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+/* Issues the copies; whole 16 byte units travel as cp.async (LDGSTS, L2 only), so the rows of the next segment
+   are in flight while the current one is being coded. The caller commits and waits. */
 template <typename T>
 __device__ __forceinline__ void stage_rows(const EncArgs &a, const uint8_t *src, uint8_t *stage,
                                            uint32_t y0, uint32_t xs, uint32_t npix)
@@ -76,7 +86,7 @@ __device__ __forceinline__ void stage_rows(const EncArgs &a, const uint8_t *src,
             const uint8_t *ga = g - mis + 16 * (size_t)u;
             uint8_t *sa = stage + r * a.rowpitch + 16 * u;
             if (ga >= g && ga + 16 <= g + rowbytes)
-                *reinterpret_cast<uint4 *>(sa) = ld_stream16(ga);
+                cp_async16(sa, ga);
             else
                 for (int b = 0; b < 16; b++)
                     if (ga + b >= g && ga + b < g + rowbytes) sa[b] = ga[b];
@@ -320,7 +330,27 @@ template <typename W> struct IndexTable {
     }
 };
 
-template <typename T, bool BEST>
+/* nibble i of the scan curve; a compile time constant for the two curves the encoder itself uses */
+template <int CURVE> __device__ __forceinline__ uint32_t curve_pos(uint64_t order, int i)
+{
+    if (CURVE == 1) return (uint32_t)(HILBERT >> (4 * (15 - i))) & 15;
+    if (CURVE == 2) return (uint32_t)(ZCURVE >> (4 * (15 - i))) & 15;
+    return (uint32_t)(order >> (4 * (15 - i))) & 15;
+}
+
+/* rung >= 1 code of a value below 2^17 in 32 bit arithmetic, packed (len << 20) | bits; no middle swap */
+__device__ __forceinline__ uint32_t packed_code32(uint32_t v, uint32_t r)
+{
+    const uint32_t top = v >> r, nxt = (v >> (r - 1)) & 1, tn = top | nxt;
+    const uint32_t payload = v & (((1u << (r - 1)) << top) - 1);
+    return ((r + tn + top) << 20) | (payload << (1 + tn)) | tn | (top << 1);
+}
+
+/* first entry of rung r (1..7) in the shared code table: 2^(r+1) entries per rung */
+__device__ __forceinline__ uint32_t lut_base(uint32_t r) { return (2u << r) - 4; }
+constexpr uint32_t LUT_ENTRIES = 508;
+
+template <typename T, bool BEST, int CURVE>
 __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ EncArgs a)
 {
     typedef typename traits<T>::W W;
@@ -330,8 +360,8 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
 
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *win = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *stage = smem + (size_t)a.win_words * 4;
-    unsigned long long *carry_prev = reinterpret_cast<unsigned long long *>(stage + 4 * (size_t)a.rowpitch); /* [2][bands] */
+    uint8_t *stage = smem + (size_t)a.win_words * 4;                                                   /* [2][4][rowpitch] */
+    unsigned long long *carry_prev = reinterpret_cast<unsigned long long *>(stage + 8 * (size_t)a.rowpitch); /* [2][bands] */
     uint32_t *scan_scratch = reinterpret_cast<uint32_t *>(carry_prev + 2 * a.bands);                   /* [33] */
     uint8_t *carry_rung = reinterpret_cast<uint8_t *>(scan_scratch + 36);                              /* [2][bands] */
     uint8_t *rung_s = carry_rung + 2 * a.bands;                                                        /* [blockDim] */
@@ -340,6 +370,11 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
     unsigned long long *cfm2_s = reinterpret_cast<unsigned long long *>(smem + a.best_off);            /* [blockDim] */
     unsigned long long *carry_pcf = cfm2_s + blockDim.x;                                               /* [2][bands] */
     int *commit_s = reinterpret_cast<int *>(carry_pcf + 2 * a.bands);                                  /* [blockDim] */
+    /* 8 / 16 bit FTL and BASE: the rung 1..7 group codes (middle swap included) and the rung switches as shared
+       tables, generated here from the closed forms; (len << 20) | bits and (len << 12) | bits */
+    constexpr bool USE_LUT = !BEST && BITS <= 16;
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + a.lut_off);                                     /* [508] */
+    uint16_t *cs_lut = reinterpret_cast<uint16_t *>(lut + LUT_ENTRIES);                                 /* [2^U] */
 
     const uint32_t tid = threadIdx.x, NT = blockDim.x, tile = blockIdx.x;
     const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
@@ -354,6 +389,13 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
         if (BEST) carry_pcf[c] = st ? st[2 * a.bands + c] : 0ull;
     }
     for (uint32_t i = tid; i < a.win_words; i += NT) win[i] = 0;
+    if (USE_LUT) {
+        for (uint32_t i = tid; i < LUT_ENTRIES; i += NT) {
+            const uint32_t r = topbit32(i + 4) - 1, v = i - lut_base(r);
+            lut[i] = packed_code32(mswap<uint32_t>(v, r), r);
+        }
+        for (uint32_t i = tid; i < (1u << U); i += NT) cs_lut[i] = (uint16_t)cs_entry(U, i);
+    }
     __syncthreads();
     for (uint32_t i = tid; i < a.hdr_len; i += NT) reinterpret_cast<uint8_t *>(win)[i] = a.hdr[i];
 
@@ -362,18 +404,34 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
     bool overflow = false;             /* output would not fit the slot: the tile ends up stored */
     uint32_t it = 0;
 
+    const uint32_t blk = tid / a.bands, c = tid - blk * a.bands; /* this thread's block in the segment and band */
+    const uint32_t stage_bytes = 4 * a.rowpitch;
+    /* segment (by, sg) -> staged rows; issued one segment ahead */
+    auto issue = [&](uint32_t by, uint32_t sg, uint32_t buf) {
+        const uint32_t bx0 = sg * a.seg_blocks, nblk = min(a.seg_blocks, a.nbx - bx0);
+        const uint32_t xs = min(4 * bx0, a.vw - 4), xe = min(4 * (bx0 + nblk), a.vw);
+        stage_rows<T>(a, src, stage + buf * stage_bytes, min(4 * by, a.vh - 4), xs, xe - xs);
+    };
+    if (a.small != 3) issue(0, 0, 0);
+    cp_async_commit();
+
     /* a.small == 3: sixteen pixels or fewer are stored outright (reference: QB3encode.cpp:490-491) */
     for (uint32_t by = 0; by < a.nby && a.small != 3; by++) {
         const uint32_t y0 = min(4 * by, a.vh - 4);
         for (uint32_t sg = 0; sg < a.segs; sg++, it++) {
             const uint32_t bx0 = sg * a.seg_blocks, nblk = min(a.seg_blocks, a.nbx - bx0), ng = nblk * a.bands;
-            const uint32_t xs = min(4 * bx0, a.vw - 4), xe = min(4 * (bx0 + nblk), a.vw);
-            stage_rows<T>(a, src, stage, y0, xs, xe - xs);
-            __syncthreads(); /* also orders the header / carry writes before their first use */
+            const uint32_t xs = min(4 * bx0, a.vw - 4);
+            const uint32_t par = it & 1;
+            {   /* next segment's rows start travelling now; this segment's have had a whole iteration to land */
+                const uint32_t nsg = sg + 1 < a.segs ? sg + 1 : 0, nby = nsg ? by : by + 1;
+                if (nby < a.nby) issue(nby, nsg, par ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+            }
+            __syncthreads(); /* also orders the header / carry / table writes before their first use */
+            const uint8_t *sbuf = stage + par * stage_bytes;
 
             const bool active = tid < ng;
-            const uint32_t blk = tid / a.bands, c = tid - blk * a.bands;
-            const uint32_t par = it & 1;
             W m[16];
             W bitsused = 0;
             uint32_t rung = 0;
@@ -388,20 +446,29 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
                     rowoff[r] = r * a.rowpitch + mis;
                 }
                 const W TM = (W)lowmask64(BITS);
+                const bool derived = cb != c;
+                /* per row: this block's first pixel, own band and core band */
+                const T *own[4], *core[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const T *p = reinterpret_cast<const T *>(sbuf + rowoff[r]) + (x0 - xs) * a.bands;
+                    own[r] = p + c;
+                    core[r] = p + cb;
+                }
                 W prv;
                 if (blk > 0) { /* last value of the previous block: curve position 15 */
-                    const uint32_t n15 = (uint32_t)a.order & 15;
-                    const T *p = reinterpret_cast<const T *>(stage + rowoff[n15 >> 2]) + (size_t)(4 * (bx - 1) - xs + (n15 & 3)) * a.bands;
-                    prv = (W)p[c];
-                    if (cb != c) prv = (prv - (W)p[cb]) & TM;
+                    const uint32_t n15 = curve_pos<CURVE>(a.order, 15);
+                    const int back = (int)((4 * (bx - 1) + (n15 & 3)) - x0) * (int)a.bands;
+                    prv = (W)own[n15 >> 2][back];
+                    if (derived) prv = (prv - (W)core[n15 >> 2][back]) & TM;
                 }
                 else prv = (W)carry_prev[par * a.bands + c] & TM;
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    const uint32_t n = (uint32_t)(a.order >> (4 * (15 - i))) & 15;
-                    const T *p = reinterpret_cast<const T *>(stage + rowoff[n >> 2]) + (size_t)(x0 - xs + (n & 3)) * a.bands;
-                    W v = (W)p[c];
-                    if (cb != c) v = (v - (W)p[cb]) & TM;
+                    const uint32_t n = curve_pos<CURVE>(a.order, i);
+                    const uint32_t px = (n & 3) * a.bands;
+                    W v = (W)own[n >> 2][px];
+                    if (derived) v = (v - (W)core[n >> 2][px]) & TM;
                     m[i] = mags<BITS, W>(v - prv);
                     prv = v;
                     bitsused |= m[i];
@@ -423,12 +490,32 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
             W cf = 1, cm2 = 0;
             if (active) {
                 oldrung = blk > 0 ? rung_s[tid - a.bands] : carry_rung[par * a.bands + c];
-                cs = switch_entry<U>(rung, oldrung);
+                cs = USE_LUT ? cs_lut[(rung - oldrung) & UMASK] : switch_entry<U>(rung, oldrung);
             }
             if (!BEST) {
                 if (active) {
                     len = cs >> 12;
                     if (bitsused <= 1) len += 1 + (bitsused ? 16 : 0); /* reference: QB3encode.h:159-166 */
+                    else if (USE_LUT) {
+                        /* every value becomes its packed code, (len << 20) | bits: the table holds the swapped rung 1..7
+                           codes, higher rungs (16 bit data) are computed */
+                        if (use_step) {
+                            const int k = step_index<W>(m, rung);
+#pragma unroll
+                            for (int i = 0; i < 16; i++) if (i == k) m[i] ^= (W)1 << rung;
+                        }
+                        if (rung < 8) {
+                            const uint32_t *t = lut + lut_base(rung);
+#pragma unroll
+                            for (int i = 0; i < 16; i++) m[i] = (W)t[(uint32_t)m[i]];
+                        }
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) m[i] = (W)packed_code32((uint32_t)m[i], rung);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i++) len += (uint32_t)m[i] >> 20;
+                    }
                     else {
                         prepare_group<W>(m, rung, use_step);
 #pragma unroll
@@ -569,6 +656,10 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
                         for (int i = 0; i < 16; i++) b |= (uint32_t)m[i] << (i + 1);
                     }
                     pk.put32(b, bitsused ? 17 : 1);
+                }
+                else if (USE_LUT) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) pk.put32((uint32_t)m[i] & 0xfffffu, (uint32_t)m[i] >> 20);
                 }
                 else {
 #pragma unroll
@@ -745,7 +836,9 @@ __global__ void __launch_bounds__(128) rle_kernel(const __grid_constant__ EncArg
 template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st)
 {
     const bool best = a.mode == M_CF_Z || a.mode == M_CF_H;
-    auto kern = best ? encode_kernel<T, true> : encode_kernel<T, false>;
+    const int curve = a.order == HILBERT ? 1 : a.order == ZCURVE ? 2 : 0;
+    auto kern = best ? (curve == 1 ? encode_kernel<T, true, 1> : curve == 2 ? encode_kernel<T, true, 2> : encode_kernel<T, true, 0>)
+                     : (curve == 1 ? encode_kernel<T, false, 1> : curve == 2 ? encode_kernel<T, false, 2> : encode_kernel<T, false, 0>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<(unsigned)ntiles, threads, smem, st>>>(a);

@@ -9,7 +9,7 @@
 
 namespace qb3 {
 cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st);
-cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st);
+cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st, uint32_t &launches);
 
 static thread_local int g_last_cuda_error = 0;
 static std::atomic<uint64_t> g_launches(0);
@@ -199,8 +199,9 @@ int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uin
     a.w = cfg->width; a.h = cfg->height; a.bands = cfg->bands; a.dtype = cfg->dtype;
     a.ref_compat = ref_compat != 0;
     a.ntiles = (uint32_t)ntiles;
-    cudaError_t err = launch_decode(a, tsize, static_cast<cudaStream_t>(stream));
-    if (err == cudaSuccess) count_launches(2);
+    uint32_t launches = 0;
+    cudaError_t err = launch_decode(a, tsize, static_cast<cudaStream_t>(stream), launches);
+    count_launches(launches);
     return note_cuda(err);
 }
 

@@ -13,6 +13,8 @@
  * quantisation element-wise over the tiles with coalesced accesses, which is what the reference does
  * per block row (QB3decode.h:730-737) and at the end (QB3decode.cpp:434-450).
  */
+#include <cstdlib>
+
 #include "qb3_device.cuh"
 
 namespace qb3 {
@@ -175,43 +177,33 @@ __device__ static uint64_t derle_size(const uint8_t *p, uint64_t len)
 
 
 /*
- * Register bit buffer for the fast path (8 and 16 bit types, no RLE): 64 bits of look-ahead fed by aligned 32 bit
- * loads with one word of read-ahead, so the load latency stays off the parse chain. After refill() at least 33 bits
- * are valid, which covers every field of these types (a code is at most 17 bits). Zero fill past the end.
+ * Bit buffer of the walk kernel (8 and 16 bit types): 64 bits of look-ahead in registers fed one 32 bit word at a
+ * time from the stream's ring in shared memory, with one word of read-ahead so the shared memory latency stays off
+ * the parse chain. After refill() at least 33 bits are valid, which covers every field of these types (a code is at
+ * most 17 bits). All lanes that share a stream hold the same state.
  */
-struct FastBits {
-    const uint32_t *base;
+struct WalkBits {
+    const uint32_t *ring;
     uint64_t buf;
-    uint32_t nwords, k, tailmask, mis8, nb, nxt;
+    uint32_t nb, nxt, k, ringmask, w0, sh;
 
-    __device__ __forceinline__ uint32_t load(uint32_t i) const
+    __device__ __forceinline__ void open(const uint32_t *r, uint32_t mask, uint32_t mis)
     {
-        uint32_t w = i < nwords ? __ldg(base + i) : 0u;
-        if (i + 1 == nwords) w &= tailmask;
-        return w;
-    }
-    __device__ __forceinline__ void open(const uint8_t *p, uint64_t len)
-    {
-        const uint32_t mis = (uint32_t)((uintptr_t)p & 3);
-        const uint64_t span = mis + len;
-        const uint32_t tail = (uint32_t)span & 3;
-        base = reinterpret_cast<const uint32_t *>(p - mis);
-        nwords = (uint32_t)((span + 3) >> 2);
-        tailmask = tail ? (1u << (8 * tail)) - 1 : 0xffffffffu;
-        mis8 = 8 * mis;
-        buf = (uint64_t)(load(0) >> mis8);
-        nb = 32 - mis8;
-        buf |= (uint64_t)load(1) << nb;
+        ring = r; ringmask = mask;
+        w0 = mis >> 2; sh = 8 * (mis & 3);
+        buf = (uint64_t)(ring[w0] >> sh);
+        nb = 32 - sh;
+        buf |= (uint64_t)ring[w0 + 1] << nb;
         nb += 32;
-        nxt = load(2);
-        k = 3;
+        nxt = ring[w0 + 2];
+        k = w0 + 3;
     }
     __device__ __forceinline__ void refill()
     {
         if (nb <= 32) {
             buf |= (uint64_t)nxt << nb;
             nb += 32;
-            nxt = load(k);
+            nxt = ring[k & ringmask];
             k++;
         }
     }
@@ -224,8 +216,24 @@ struct FastBits {
         advance(n);
         return v;
     }
-    __device__ __forceinline__ uint64_t consumed() const { return 32ull * (k - 1) - mis8 - nb; }
+    __device__ __forceinline__ uint64_t consumed() const { return 32ull * (k - 1 - w0) - sh - nb; }
 };
+
+/* dequantize (reference: QB3decode.cpp:77-107): multiply by quanta, saturating at the type's range */
+template <int BITS> __device__ __forceinline__ uint64_t dequantize_value(uint64_t v, uint64_t q, bool is_signed)
+{
+    const uint64_t UM = lowmask64(BITS);
+    if (!is_signed) return v <= UM / q ? v * q : UM;
+    const long long smax = (long long)(UM >> 1), smin = -smax - 1;
+    const long long d = (long long)(v << (64 - BITS)) >> (64 - BITS);
+    long long t = d <= smax / (long long)q ? (long long)((uint64_t)d * q) : smax;
+    if (q > 2 && d < smin / (long long)q) t = smin;
+    return (uint64_t)t & UM;
+}
+
+/* tile states that only live between the decode kernels of one batch */
+constexpr uint32_t ST_DEFER = 0x80000000u;  /* walk_kernel left the tile to the general path */
+constexpr uint32_t ST_FINISH = 0x40000000u; /* pixels are in place but still band differenced / quantised */
 
 /* ------------------------------------------------------------------ group parse */
 
@@ -360,139 +368,282 @@ __device__ __noinline__ bool read_special_group(S &s, W (&g)[16], uint8_t &rb, W
 }
 
 /*
- * Fast path: 8 and 16 bit types, no RLE, regular geometry. Same parse as the general path, but
- *  - bits come from the register buffer above, values are decoded with rung-uniform 32 bit arithmetic
- *    (no tables, no rung branches inside the 16 value loop)
- *  - pixels are not scattered to global memory one by one: each lane owns four staged rows of a few blocks
- *    in shared memory (odd word stride between lanes, so no bank conflicts) and writes them out as whole
- *    words when the staging group is full. Groups wider than the staging budget are written directly.
+ * The decode kernel for 8 and 16 bit types: a warp walks 32 / LPS streams, LPS lanes each.
+ *
+ * A stream is one serial bit parse (every code's position depends on the two low bits of the code before it and
+ * there is no index in the format), so what bounds a stream is the latency of that chain, and what bounds the
+ * batch is how many streams are in flight and how few issue slots each one takes. Hence:
+ *  - the lanes of a stream all run the chain (the same instructions, so the redundancy is free) and keep only the
+ *    codes of their own 16 / LPS values; values, step undo, sign unfolding, the running sum (a shuffle scan) and
+ *    the scatter into the staged rows are then split between the lanes
+ *  - the compressed bytes travel HBM -> registers -> shared memory ring in 16 byte units per lane, half a ring
+ *    ahead of the parse position, so no global load latency is ever on the chain
+ *  - pixels are staged per stream for a run of blocks (four image rows), get their core band added and their
+ *    quanta multiplied there (QB3decode.h:730-737, QB3decode.cpp:77-107), and leave as whole 16 byte vectors
+ * Streams this kernel does not take (stored, RLE, bad headers) are left to the general path through the tile status.
  */
-template <typename T, bool STAGED>
-__device__ bool decode_fast(const DecArgs &a, const StreamInfo &info, const uint8_t *payload, uint64_t plen, T *out,
-                            uint32_t *prev, uint32_t *pcf, uint8_t *runbits, uint8_t *stage, uint32_t lane_stride,
-                            uint32_t stage_blocks)
+template <typename T, int LPS>
+__global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_t stage_blocks, const uint32_t stage_off,
+                                                  const uint32_t sstride)
 {
     typedef uint32_t W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
     constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
     constexpr W TM = (W)((1ull << BITS) - 1);
-    const uint32_t lane = threadIdx.x;
-    const uint64_t order = info.order ? info.order : HILBERT;
-    const bool ftl = info.mode == M_FTL;
-    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, bands = a.bands;
+    constexpr int NS = 32 / LPS, VPL = 16 / LPS, HW = 4 * LPS, RW = 2 * HW;
+    constexpr int VPR = BITS == 8 ? 3 : 2; /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
+    constexpr uint32_t FULL = 0xffffffffu;
 
-    FastBits s;
-    s.open(payload, plen);
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint16_t *dsw = reinterpret_cast<uint16_t *>(smem); /* rung switch decode table, 2^(U+1) entries */
+    const uint32_t lane = threadIdx.x, sub = lane / LPS, sl = lane % LPS;
+    const uint32_t submask = LPS == 32 ? FULL : ((1u << LPS) - 1) << (sub * LPS);
+    uint8_t *mine = smem + 64 + (size_t)sub * sstride;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(mine);
+    uint32_t *prev = ring + RW, *pcf = prev + a.bands;
+    uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + a.bands), *cb = rb + a.bands;
+    T *stage = reinterpret_cast<T *>(mine + stage_off);
+    const uint32_t bands = a.bands;
+    const bool staged = stage_blocks != 0;
 
-    /* element offsets of the 16 curve positions inside the destination of a block */
-    const uint32_t rowelems = STAGED ? stage_blocks * 4 * bands : (uint32_t)a.stride;
-    uint32_t off[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t n = (uint32_t)(order >> (4 * (15 - i))) & 15;
-        off[i] = (n >> 2) * rowelems + (n & 3) * bands;
+    for (uint32_t i = lane; i < (2u << U); i += 32) dsw[i] = (uint16_t)ds_entry(U, i);
+
+    const uint32_t tile = blockIdx.x * NS + sub;
+    const bool live = tile < a.ntiles;
+    const uint8_t *stream = nullptr;
+    uint64_t slen = 0;
+    StreamInfo info;
+    info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
+    if (live) {
+        stream = a.streams + a.offsets[tile];
+        slen = a.lens[tile];
+        if (sl == 0) parse_header(stream, slen, a, info, cb, 1);
     }
-    T *const lane_stage = reinterpret_cast<T *>(stage + (size_t)lane * lane_stride);
-    for (uint32_t c = 0; c < bands; c++) { prev[c * 32 + lane] = 0; pcf[c * 32 + lane] = 0; runbits[c * 32 + lane] = 0; }
+    __syncwarp();
+    info.bad = __shfl_sync(FULL, info.bad, 0, LPS);
+    info.mode = __shfl_sync(FULL, info.mode, 0, LPS);
+    info.data_off = __shfl_sync(FULL, info.data_off, 0, LPS);
+    info.order = __shfl_sync(FULL, info.order, 0, LPS);
+    info.quanta = __shfl_sync(FULL, info.quanta, 0, LPS);
+    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
+    const bool go = live && !info.bad && info.mode != M_STORED && !rle;
+    if (live && !go && sl == 0) a.status[tile] = info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
 
-    bool failed = false;
-    for (uint32_t by = 0; by < nby && !failed; by++) {
-        const uint32_t y0 = min(4 * by, a.h - 4);
-        for (uint32_t gb = 0; gb < nbx && !failed; gb += stage_blocks) {
-            const uint32_t gend = min(nbx, gb + stage_blocks);
-            const uint32_t xs = min(4 * gb, a.w - 4), xe = min(4 * gend, a.w);
-            for (uint32_t bx = gb; bx < gend && !failed; bx++) {
-                const uint32_t x0 = min(4 * bx, a.w - 4);
-                for (uint32_t c = 0; c < bands; c++) {
-                    W g[16];
-                    uint32_t cs = 0;
-                    s.refill();
-                    if (s.buf & 1) {
-                        cs = ds_entry(U, (uint32_t)(s.buf >> 1) & LMASK);
-                        s.advance(cs >> 12);
-                    }
-                    else s.advance(1);
-                    if (ftl || (cs & 0xfff) != 0 || cs == 0) {
-                        const uint32_t r = (runbits[c * 32 + lane] + cs) & UMASK;
-                        runbits[c * 32 + lane] = (uint8_t)r;
-                        if (r == 0) { /* flag, then 16 raw bits (reference: QB3decode.h:148-160) */
-                            s.refill();
-                            const uint32_t x = (uint32_t)s.buf;
-                            const uint32_t b = (x & 1) ? (x >> 1) & 0xffffu : 0u;
-                            s.advance((x & 1) ? 17 : 1);
+    /* the payload as 16 byte chunks from an aligned base; bytes past the end read as zero (bitstream.h:43-49) */
+    const uint8_t *payload = go ? stream + info.data_off : nullptr;
+    const uint64_t plen = go ? slen - info.data_off : 0;
+    const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
+    const uint8_t *abase = payload - mis;
+    const uint64_t span = go ? mis + plen : 0;
+    auto load_chunk = [&](uint32_t ci) -> uint4 {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        const uint64_t start = 16ull * ci;
+        if (start < span) {
+            v = ld_stream16(abase + start);
+            if (start + 16 > span) {
+                const uint32_t rem = (uint32_t)(span - start); /* 1..15 valid bytes */
+                uint32_t *w = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
-                            for (int i = 0; i < 16; i++) g[i] = (b >> i) & 1;
-                        }
-                        else {
-                            const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
-                            uint32_t M = 0;
-#pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                s.refill();
-                                const uint32_t x = (uint32_t)s.buf;
-                                const uint32_t b0 = x & 1, t = b0 & (x >> 1);
-                                const uint32_t ht = half << t;
-                                uint32_t v = ((x >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
-                                s.advance(r + b0 + t);
-                                if (v - fm1 <= 1u) v ^= sm; /* middle swap at rungs 1..7 */
-                                g[i] = v;
-                                M |= ((v >> r) & 1u) << i;
-                            }
-                            if (!ftl) {
-                                const int k = step_decode_index(M);
-#pragma unroll
-                                for (int i = 0; i < 16; i++) if (i == k) g[i] ^= 1u << r;
-                            }
-                        }
-                    }
-                    else { /* rare: keep the by-reference array of the out-of-line call away from the hot registers */
-                        W sg[16];
-                        if (read_special_group<W, BITS, U>(s, sg, runbits[c * 32 + lane], pcf[c * 32 + lane])) { failed = true; break; }
-#pragma unroll
-                        for (int i = 0; i < 16; i++) g[i] = sg[i];
-                    }
-
-                    W prv = prev[c * 32 + lane];
-                    T *dstp = STAGED ? lane_stage + (size_t)(x0 - xs) * bands + c
-                                     : out + (uint64_t)y0 * a.stride + (uint64_t)x0 * bands + c;
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        prv = (prv + smag<BITS, W>(g[i])) & TM;
-                        dstp[off[i]] = (T)prv;
-                    }
-                    prev[c * 32 + lane] = prv;
-                }
-            }
-            if (STAGED && !failed) { /* staged rows leave as whole words when the destination allows */
-                const uint32_t rowbytes = (xe - xs) * bands * (uint32_t)sizeof(T), srow = rowelems * (uint32_t)sizeof(T);
-                for (uint32_t r = 0; r < 4; r++) {
-                    uint8_t *gp = reinterpret_cast<uint8_t *>(out + (uint64_t)(y0 + r) * a.stride + (uint64_t)xs * bands);
-                    const uint8_t *sp = reinterpret_cast<const uint8_t *>(lane_stage) + r * srow;
-                    if ((((uintptr_t)gp | rowbytes) & 15) == 0) {
-                        for (uint32_t j = 0; j < rowbytes; j += 16) {
-                            const uint32_t *w = reinterpret_cast<const uint32_t *>(sp + j);
-                            *reinterpret_cast<uint4 *>(gp + j) = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    }
-                    else if ((((uintptr_t)gp | rowbytes) & 3) == 0) {
-                        for (uint32_t j = 0; j < rowbytes; j += 4)
-                            *reinterpret_cast<uint32_t *>(gp + j) = *reinterpret_cast<const uint32_t *>(sp + j);
-                    }
-                    else {
-                        for (uint32_t j = 0; j < rowbytes; j += sizeof(T))
-                            *reinterpret_cast<T *>(gp + j) = *reinterpret_cast<const T *>(sp + j);
-                    }
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t lo = 4 * j;
+                    if (rem <= lo) w[j] = 0;
+                    else if (rem < lo + 4) w[j] &= (1u << (8 * (rem - lo))) - 1;
                 }
             }
         }
+        return v;
+    };
+
+    /* per band running state; does any band need the core band added, or the quanta multiplied, at the flush */
+    for (uint32_t c = sl; c < bands; c += LPS) { prev[c] = 0; pcf[c] = 0; rb[c] = 0; }
+    uint4 *ring4 = reinterpret_cast<uint4 *>(ring);
+    ring4[sl] = load_chunk(sl);
+    ring4[LPS + sl] = load_chunk(LPS + sl);
+    uint4 pend = load_chunk(2 * LPS + sl);
+    uint32_t curhalf = 0;
+    __syncwarp();
+    uint32_t derived = 0;
+    if (go) for (uint32_t c = sl; c < bands; c += LPS) derived |= cb[c] != c;
+#pragma unroll
+    for (int d = 1; d < LPS; d <<= 1) derived |= __shfl_xor_sync(FULL, derived, d, LPS);
+    const uint64_t quanta = info.quanta;
+    const bool fix = go && (derived || quanta > 1), is_signed = a.dtype & 1;
+
+    WalkBits s;
+    s.open(ring, RW - 1, mis);
+
+    const uint64_t order = info.order ? info.order : HILBERT;
+    const bool ftl = info.mode == M_FTL;
+    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4;
+    const uint32_t sblocks = staged ? stage_blocks : 1;
+    const uint32_t rowelems = staged ? stage_blocks * 4 * bands : (uint32_t)a.stride;
+    uint32_t off[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+        const uint32_t n = (uint32_t)(order >> (4 * (15 - (sl * VPL + j)))) & 15;
+        off[j] = (n >> 2) * rowelems + (n & 3) * bands;
     }
-    if (failed) return true;
-    const uint64_t total = 8 * plen, used = s.consumed();
-    return total > used && total - used > 7; /* reference: QB3decode.h:411,740 */
+    T *out = reinterpret_cast<T *>(a.dst + (uint64_t)(live ? tile : 0) * a.dst_pitch);
+
+    bool failed = false;
+    for (uint32_t by = 0; by < nby; by++) {
+        const uint32_t y0 = min(4 * by, a.h - 4);
+        for (uint32_t gb = 0; gb < nbx; gb += sblocks) {
+            const uint32_t gend = min(nbx, gb + sblocks);
+            const uint32_t xs = min(4 * gb, a.w - 4), xe = min(4 * gend, a.w);
+            for (uint32_t bx = gb; bx < gend; bx++) {
+                const uint32_t x0 = min(4 * bx, a.w - 4);
+                for (uint32_t c = 0; c < bands; c++) {
+                    /* ring upkeep: on entering a half, the chunks held back in registers replace the half just left
+                       and the loads for the half after that start */
+                    const uint32_t hnow = s.k / HW;
+                    if (hnow != curhalf) {
+                        curhalf = hnow;
+                        __syncwarp(submask);
+                        ring4[((hnow + 1) & 1) * LPS + sl] = pend;
+                        pend = load_chunk((hnow + 2) * LPS + sl);
+                        __syncwarp(submask);
+                    }
+                    const W pv = prev[c];
+                    const uint32_t oldrung = rb[c];
+
+                    s.refill();
+                    const uint32_t x = (uint32_t)s.buf;
+                    uint32_t cs = 0;
+                    if (x & 1) cs = dsw[(x >> 1) & LMASK];
+                    s.advance((x & 1) ? cs >> 12 : 1);
+
+                    W v[VPL];
+                    if (ftl || (cs & 0xfff) != 0 || cs == 0) {
+                        const uint32_t r = (oldrung + cs) & UMASK;
+                        rb[c] = (uint8_t)r;
+                        if (r == 0) { /* flag, then 16 raw bits (reference: QB3decode.h:148-160) */
+                            s.refill();
+                            const uint32_t y = (uint32_t)s.buf;
+                            const uint32_t b = (y & 1) ? (y >> 1) & 0xffffu : 0u;
+                            s.advance((y & 1) ? 17 : 1);
+#pragma unroll
+                            for (int j = 0; j < VPL; j++) v[j] = (b >> (sl * VPL + j)) & 1;
+                        }
+                        else {
+                            uint32_t code[VPL];
+#pragma unroll
+                            for (int j = 0; j < VPL; j++) code[j] = 0;
+                            const bool every = BITS == 16 && r == 15; /* two 17 bit codes exceed what one refill promises */
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                if (i % VPR == 0 || every) s.refill();
+                                const uint32_t lo = (uint32_t)s.buf;
+                                const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
+                                if (sl == i / VPL) code[i % VPL] = lo;
+                                s.advance(r + b0 + t);
+                            }
+                            const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
+#pragma unroll
+                            for (int j = 0; j < VPL; j++) {
+                                const uint32_t y = code[j], b0 = y & 1, t = b0 & (y >> 1), ht = half << t;
+                                uint32_t val = ((y >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
+                                if (val - fm1 <= 1u) val ^= sm; /* middle swap at rungs 1..7 */
+                                v[j] = val;
+                            }
+                            if (!ftl) { /* step undo (reference: QB3decode.h:285-289); value i lives in lane i / VPL, slot i % VPL */
+                                uint32_t kk = 0, ok = 1, m[VPL];
+#pragma unroll
+                                for (int j = 0; j < VPL; j++) {
+                                    m[j] = (__ballot_sync(submask, (v[j] >> r) & 1) >> (sub * LPS)) & (LPS == 32 ? FULL : (1u << LPS) - 1);
+                                    kk += __popc(m[j]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < VPL; j++) ok &= m[j] == (1u << ((kk + VPL - 1 - j) / VPL)) - 1;
+                                if (ok && kk < 16) {
+#pragma unroll
+                                    for (int j = 0; j < VPL; j++) if (sl * VPL + j == kk) v[j] ^= 1u << r;
+                                }
+                            }
+                        }
+                    }
+                    else { /* common factor or index group: every lane parses it, then keeps its own values */
+                        W sg[16];
+                        uint8_t rbv = (uint8_t)oldrung;
+                        W pc = pcf[c];
+                        failed |= read_special_group<W, BITS, U>(s, sg, rbv, pc);
+                        rb[c] = rbv;
+                        pcf[c] = pc;
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) {
+                            W t = 0;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) if (sl * VPL + j == i) t = sg[i];
+                            v[j] = t;
+                        }
+                    }
+
+                    /* undo the running delta: local sums, then an exclusive scan over the stream's lanes */
+                    W acc[VPL], tot = 0;
+#pragma unroll
+                    for (int j = 0; j < VPL; j++) { tot += smag<BITS, W>(v[j]); acc[j] = tot; }
+                    W inc = tot;
+#pragma unroll
+                    for (int d = 1; d < LPS; d <<= 1) {
+                        const W o = __shfl_up_sync(submask, inc, d, LPS);
+                        if (sl >= d) inc += o;
+                    }
+                    const W base = pv + inc - tot;
+                    prev[c] = (pv + __shfl_sync(submask, inc, LPS - 1, LPS)) & TM;
+                    T *dstp = staged ? stage + (size_t)(x0 - xs) * bands + c
+                                     : out + (uint64_t)y0 * a.stride + (uint64_t)x0 * bands + c;
+                    if (staged || go) {
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) dstp[off[j]] = (T)((base + acc[j]) & TM);
+                    }
+                }
+            }
+            if (!staged) continue;
+            __syncwarp();
+            const uint32_t npx = xe - xs;
+            if (fix) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
+                for (uint32_t r = 0; r < 4; r++)
+                    for (uint32_t px = sl; px < npx; px += LPS) {
+                        T *p = stage + (size_t)r * rowelems + (size_t)px * bands;
+                        if (derived)
+                            for (uint32_t c = 0; c < bands; c++) {
+                                const uint32_t k = cb[c];
+                                if (k != c) p[c] = (T)(p[c] + p[k]);
+                            }
+                        if (quanta > 1)
+                            for (uint32_t c = 0; c < bands; c++)
+                                p[c] = (T)dequantize_value<BITS>((uint64_t)p[c], quanta, is_signed);
+                    }
+                __syncwarp();
+            }
+            if (go) { /* staged rows leave as the widest vectors the destination allows */
+                const uint32_t rowbytes = npx * bands * (uint32_t)sizeof(T), srow = rowelems * (uint32_t)sizeof(T);
+                for (uint32_t r = 0; r < 4; r++) {
+                    uint8_t *gp = reinterpret_cast<uint8_t *>(out + (uint64_t)(y0 + r) * a.stride + (uint64_t)xs * bands);
+                    const uint8_t *sp = reinterpret_cast<const uint8_t *>(stage) + r * srow;
+                    if ((((uintptr_t)gp | rowbytes) & 15) == 0)
+                        for (uint32_t j = 16 * sl; j < rowbytes; j += 16 * LPS)
+                            *reinterpret_cast<uint4 *>(gp + j) = *reinterpret_cast<const uint4 *>(sp + j);
+                    else if ((((uintptr_t)gp | rowbytes) & 3) == 0)
+                        for (uint32_t j = 4 * sl; j < rowbytes; j += 4 * LPS)
+                            *reinterpret_cast<uint32_t *>(gp + j) = *reinterpret_cast<const uint32_t *>(sp + j);
+                    else
+                        for (uint32_t j = sizeof(T) * sl; j < rowbytes; j += sizeof(T) * LPS)
+                            *reinterpret_cast<T *>(gp + j) = *reinterpret_cast<const T *>(sp + j);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (go && sl == 0) {
+        const uint64_t total = 8 * plen, used = s.consumed();
+        const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
+        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : (!staged && fix) ? ST_FINISH : (uint32_t)QB3CU_TILE_OK;
+    }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, uint32_t stage_off, uint32_t lane_stride, uint32_t stage_blocks)
+__global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, const bool only_deferred)
 {
     typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -508,6 +659,7 @@ __global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, uint32_t 
 
     const uint32_t lane = threadIdx.x, tile = blockIdx.x * 32 + lane;
     if (tile >= a.ntiles) return;
+    if (only_deferred && a.status[tile] != ST_DEFER) return; /* walk_kernel has dealt with it */
     const uint8_t *stream = a.streams + a.offsets[tile];
     const uint64_t slen = a.lens[tile];
     T *out = reinterpret_cast<T *>(a.dst + (uint64_t)tile * a.dst_pitch);
@@ -520,7 +672,7 @@ __global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, uint32_t 
     const uint64_t raw = (uint64_t)a.w * a.h * a.bands * sizeof(T);
 
     if (info.mode == M_STORED) { /* reference: QB3decode.cpp:356-375 */
-        a.status[tile] = plen == raw ? QB3CU_TILE_OK : QB3CU_TILE_CORRUPT; /* finish_kernel copies the pixels */
+        a.status[tile] = plen == raw ? ST_FINISH : (uint32_t)QB3CU_TILE_CORRUPT; /* finish_kernel copies the pixels */
         return;
     }
     if ((uint64_t)a.w * a.h < 16) { a.status[tile] = QB3CU_TILE_CORRUPT; return; } /* reference: QB3decode.cpp:389 */
@@ -530,14 +682,6 @@ __global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, uint32_t 
     if (rle) {
         logical = derle_size(payload, plen);
         if (logical > raw) { a.status[tile] = QB3CU_TILE_RLE_TOO_BIG; return; } /* reference: QB3decode.cpp:401 */
-    }
-    if (sizeof(T) <= 2 && !rle && a.w >= 4 && a.h >= 4) {
-        uint32_t *p32 = reinterpret_cast<uint32_t *>(prev), *c32 = reinterpret_cast<uint32_t *>(pcf);
-        const bool bad = stage_blocks
-            ? decode_fast<T, true>(a, info, payload, plen, out, p32, c32, runbits, smem + stage_off, lane_stride, stage_blocks)
-            : decode_fast<T, false>(a, info, payload, plen, out, p32, c32, runbits, nullptr, 0, 1);
-        a.status[tile] = bad ? QB3CU_TILE_CORRUPT : QB3CU_TILE_OK;
-        return;
     }
     Reader s;
     s.open(payload, plen, rle, logical);
@@ -594,7 +738,7 @@ __global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, uint32_t 
         }
     }
     if (failed || s.avail() > 7) { a.status[tile] = QB3CU_TILE_CORRUPT; return; } /* reference: QB3decode.h:740 */
-    a.status[tile] = QB3CU_TILE_OK;
+    a.status[tile] = ST_FINISH;
 }
 
 /*
@@ -611,7 +755,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const DecArgs a, uint32_t r
     __shared__ uint8_t cband[MAXBANDS];
     __shared__ uint32_t derived;
     const uint32_t tile = blockIdx.x;
-    if (a.status[tile] != QB3CU_TILE_OK) return;
+    if (a.status[tile] != ST_FINISH) return;
     if (threadIdx.x == 0) {
         parse_header(a.streams + a.offsets[tile], a.lens[tile], a, info, cband, 1);
         uint32_t d = 0;
@@ -632,10 +776,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const DecArgs a, uint32_t r
     }
     if (!derived && info.quanta < 2) return;
     const bool is_signed = a.dtype & 1;
-    const uint64_t q = info.quanta, UM = lowmask64(BITS);
-    const uint64_t umax_q = UM / q;
-    const long long smax = (long long)(UM >> 1), smin = -smax - 1;
-    const long long smax_q = smax / (long long)q, smin_q = smin / (long long)q;
+    const uint64_t q = info.quanta;
     for (uint32_t y = ybeg; y < yend; y++) {
         T *row = out + (uint64_t)y * a.stride;
         for (uint32_t x = threadIdx.x; x < a.w; x += blockDim.x) {
@@ -644,57 +785,91 @@ __global__ void __launch_bounds__(256) finish_kernel(const DecArgs a, uint32_t r
                 for (uint32_t c = 0; c < a.bands; c++)
                     if (cband[c] != c) p[c] = (T)(p[c] + p[cband[c]]);
             if (q > 1)
-                for (uint32_t c = 0; c < a.bands; c++) {
-                    const uint64_t v = (uint64_t)p[c];
-                    uint64_t r;
-                    if (is_signed) {
-                        const long long d = (long long)(v << (64 - BITS)) >> (64 - BITS);
-                        long long t = d <= smax_q ? (long long)((uint64_t)d * q) : smax;
-                        if (q > 2 && d < smin_q) t = smin;
-                        r = (uint64_t)t & UM;
-                    }
-                    else r = v <= umax_q ? v * q : UM;
-                    p[c] = (T)r;
-                }
+                for (uint32_t c = 0; c < a.bands; c++) p[c] = (T)dequantize_value<BITS>((uint64_t)p[c], q, is_signed);
         }
     }
     (void)sizeof(W);
 }
 
+/* the transient bits leave the status words */
+__global__ void __launch_bounds__(256) seal_kernel(uint32_t *status, uint32_t ntiles)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles && status[t] == ST_FINISH) status[t] = QB3CU_TILE_OK;
+}
+
 /* ------------------------------------------------------------------ launch */
 
-template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaStream_t st)
+static int walk_lanes_override()
+{
+    static const int v = [] { const char *e = getenv("QB3CU_LPS"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <typename T, int LPS>
+static cudaError_t launch_walk(const DecArgs &a, uint32_t stage_blocks, uint32_t stage_off, uint32_t sstride, cudaStream_t st)
+{
+    constexpr uint32_t NS = 32 / LPS;
+    const size_t smem = 64 + (size_t)NS * sstride;
+    cudaError_t err = cudaFuncSetAttribute(walk_kernel<T, LPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    walk_kernel<T, LPS><<<(a.ntiles + NS - 1) / NS, 32, smem, st>>>(a, stage_blocks, stage_off, sstride);
+    return cudaGetLastError();
+}
+
+/* kernels launched, for the bookkeeping of qb3cu_kernel_launches */
+template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaStream_t st, uint32_t &launches)
 {
     typedef typename traits<T>::W W;
-    size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
-    /* fast path staging: as many blocks per lane as fit 192 bytes per staged row, none when one block is wider */
-    uint32_t stage_blocks = 0, lane_stride = 0, stage_off = 0;
-    const uint32_t block_row_bytes = 4 * a.bands * (uint32_t)sizeof(T);
-    if (sizeof(T) <= 2 && block_row_bytes <= 192) {
-        stage_blocks = 192 / block_row_bytes;
-        lane_stride = 4 * stage_blocks * block_row_bytes;
-        lane_stride = ((lane_stride + 3) & ~3u) | 4; /* an odd number of words: lanes fall on different banks */
-        stage_off = (uint32_t)((smem + 15) & ~(size_t)15);
-        smem = stage_off + (size_t)32 * lane_stride;
+    cudaError_t err;
+    bool walked = false;
+    launches = 0;
+    if constexpr (sizeof(T) <= 2) if (a.w >= 4 && a.h >= 4) {
+        /* lanes per stream: the fewer streams there are, the more lanes each one can have for its parallel part */
+        int lps = walk_lanes_override();
+        if (lps != 4 && lps != 8 && lps != 16) lps = a.ntiles >= 2048 ? 8 : 16;
+        const uint32_t hw_bytes = 2 * 16 * (uint32_t)lps;
+        /* staged run of blocks: a multiple of four (rows stay 16 byte multiples) within 8 KB per stream, aiming at 2 KB */
+        const uint32_t block_bytes = 16 * a.bands * (uint32_t)sizeof(T);
+        uint32_t stage_blocks = 0;
+        if (4 * block_bytes <= 8192) {
+            stage_blocks = 4 * (2048 / (4 * block_bytes));
+            if (stage_blocks < 4) stage_blocks = 4;
+            const uint32_t nbx = (a.w + 3) / 4;
+            if (stage_blocks > ((nbx + 3) & ~3u)) stage_blocks = (nbx + 3) & ~3u;
+        }
+        const uint32_t stage_off = (hw_bytes + a.bands * 10 + 15) & ~15u;
+        const uint32_t sstride = stage_off + stage_blocks * block_bytes + 16; /* the spare vector shifts the streams' banks */
+        err = lps == 4 ? launch_walk<T, 4>(a, stage_blocks, stage_off, sstride, st)
+            : lps == 8 ? launch_walk<T, 8>(a, stage_blocks, stage_off, sstride, st)
+                       : launch_walk<T, 16>(a, stage_blocks, stage_off, sstride, st);
+        if (err != cudaSuccess) return err;
+        launches++;
+        walked = true;
     }
-    cudaError_t err = cudaFuncSetAttribute(parse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
+    err = cudaFuncSetAttribute(parse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    parse_kernel<T><<<(a.ntiles + 31) / 32, 32, smem, st>>>(a, stage_off, lane_stride, stage_blocks);
+    parse_kernel<T><<<(a.ntiles + 31) / 32, 32, smem, st>>>(a, walked);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     const uint32_t rows_per_cta = 16;
     dim3 grid(a.ntiles, (a.h + rows_per_cta - 1) / rows_per_cta);
     finish_kernel<T><<<grid, 256, 0, st>>>(a, rows_per_cta);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    seal_kernel<<<(a.ntiles + 255) / 256, 256, 0, st>>>(a.status, a.ntiles);
+    launches += 3;
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st)
+cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st, uint32_t &launches)
 {
     switch (tsize) {
-    case 1: return launch_decode_t<uint8_t>(a, st);
-    case 2: return launch_decode_t<uint16_t>(a, st);
-    case 4: return launch_decode_t<uint32_t>(a, st);
-    default: return launch_decode_t<uint64_t>(a, st);
+    case 1: return launch_decode_t<uint8_t>(a, st, launches);
+    case 2: return launch_decode_t<uint16_t>(a, st, launches);
+    case 4: return launch_decode_t<uint32_t>(a, st, launches);
+    default: return launch_decode_t<uint64_t>(a, st, launches);
     }
 }
 

@@ -182,20 +182,27 @@ __device__ static uint64_t derle_size(const uint8_t *p, uint64_t len)
  * the parse chain. After refill() at least 33 bits are valid, which covers every field of these types (a code is at
  * most 17 bits). All lanes that share a stream hold the same state.
  */
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 struct WalkBits {
-    const uint32_t *ring;
     uint64_t buf;
+    uint32_t ring;     /* shared memory address of the stream's ring */
     uint32_t nb, nxt, k, ringmask, w0, sh;
 
-    __device__ __forceinline__ void open(const uint32_t *r, uint32_t mask, uint32_t mis)
+    __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t mask, uint32_t mis)
     {
-        ring = r; ringmask = mask;
+        ring = ring_addr; ringmask = mask;
         w0 = mis >> 2; sh = 8 * (mis & 3);
-        buf = (uint64_t)(ring[w0] >> sh);
+        buf = (uint64_t)(lds32(ring + 4 * w0) >> sh);
         nb = 32 - sh;
-        buf |= (uint64_t)ring[w0 + 1] << nb;
+        buf |= (uint64_t)lds32(ring + 4 * (w0 + 1)) << nb;
         nb += 32;
-        nxt = ring[w0 + 2];
+        nxt = lds32(ring + 4 * (w0 + 2));
         k = w0 + 3;
     }
     __device__ __forceinline__ void refill()
@@ -203,7 +210,7 @@ struct WalkBits {
         if (nb <= 32) {
             buf |= (uint64_t)nxt << nb;
             nb += 32;
-            nxt = ring[k & ringmask];
+            nxt = lds32(ring + 4 * (k & ringmask));
             k++;
         }
     }
@@ -378,12 +385,14 @@ __device__ __noinline__ bool read_special_group(S &s, W (&g)[16], uint8_t &rb, W
  *    the scatter into the staged rows are then split between the lanes
  *  - the compressed bytes travel HBM -> registers -> shared memory ring in 16 byte units per lane, half a ring
  *    ahead of the parse position, so no global load latency is ever on the chain
- *  - pixels are staged per stream for a run of blocks (four image rows), get their core band added and their
- *    quanta multiplied there (QB3decode.h:730-737, QB3decode.cpp:77-107), and leave as whole 16 byte vectors
+ *  - pixels are staged per stream for a run of blocks (four image rows). The core band is added while staging
+ *    (QB3decode.h:730-737): a lane owns the same pixels in every band of a block, so a derived band that comes after
+ *    its core band adds the staged core value, and a core band adds itself to the derived bands staged before it.
+ *    Quanta are multiplied at the flush (QB3decode.cpp:77-107); rows leave as whole 16 byte vectors
  * Streams this kernel does not take (stored, RLE, bad headers) are left to the general path through the tile status.
  */
 template <typename T, int LPS>
-__global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_t stage_blocks, const uint32_t stage_off,
+__global__ void __launch_bounds__(32, 16) walk_kernel(const DecArgs a, const uint32_t stage_blocks, const uint32_t stage_off,
                                                   const uint32_t sstride)
 {
     typedef uint32_t W;
@@ -392,18 +401,21 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
     constexpr W TM = (W)((1ull << BITS) - 1);
     constexpr int NS = 32 / LPS, VPL = 16 / LPS, HW = 4 * LPS, RW = 2 * HW;
     constexpr int VPR = BITS == 8 ? 3 : 2; /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
-    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int MAXWORDS = BITS == 8 ? 6 : 12; /* ring words one group can consume, any kind */
+    constexpr int UPKEEP = (HW - 2) / MAXWORDS > 0 ? (HW - 2) / MAXWORDS : 1; /* groups between ring checks */
+    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xff;
 
     extern __shared__ __align__(16) uint8_t smem[];
     uint16_t *dsw = reinterpret_cast<uint16_t *>(smem); /* rung switch decode table, 2^(U+1) entries */
     const uint32_t lane = threadIdx.x, sub = lane / LPS, sl = lane % LPS;
     const uint32_t submask = LPS == 32 ? FULL : ((1u << LPS) - 1) << (sub * LPS);
+    const uint32_t bands = a.bands;
     uint8_t *mine = smem + 64 + (size_t)sub * sstride;
     uint32_t *ring = reinterpret_cast<uint32_t *>(mine);
-    uint32_t *prev = ring + RW, *pcf = prev + a.bands;
-    uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + a.bands), *cb = rb + a.bands;
+    uint32_t *prev = ring + RW, *pcf = prev + bands;
+    uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + bands), *cb = rb + bands;
+    uint8_t *head = cb + bands, *nextc = head + bands; /* derived bands that precede their core band, as lists */
     T *stage = reinterpret_cast<T *>(mine + stage_off);
-    const uint32_t bands = a.bands;
     const bool staged = stage_blocks != 0;
 
     for (uint32_t i = lane; i < (2u << U); i += 32) dsw[i] = (uint16_t)ds_entry(U, i);
@@ -414,10 +426,19 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
     uint64_t slen = 0;
     StreamInfo info;
     info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
+    uint32_t bandflags = 0; /* 1: some band is derived, 2: a core band is itself derived (only hand made streams) */
     if (live) {
         stream = a.streams + a.offsets[tile];
         slen = a.lens[tile];
-        if (sl == 0) parse_header(stream, slen, a, info, cb, 1);
+        if (sl == 0) {
+            parse_header(stream, slen, a, info, cb, 1);
+            for (uint32_t c = 0; c < bands; c++) head[c] = nextc[c] = (uint8_t)NONE;
+            for (uint32_t c = bands; c-- > 0;) {
+                const uint32_t k = cb[c];
+                if (k != c) bandflags |= 1 | (cb[k] != k ? 2 : 0);
+                if (k > c) { nextc[c] = head[k]; head[k] = (uint8_t)c; }
+            }
+        }
     }
     __syncwarp();
     info.bad = __shfl_sync(FULL, info.bad, 0, LPS);
@@ -425,6 +446,7 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
     info.data_off = __shfl_sync(FULL, info.data_off, 0, LPS);
     info.order = __shfl_sync(FULL, info.order, 0, LPS);
     info.quanta = __shfl_sync(FULL, info.quanta, 0, LPS);
+    bandflags = __shfl_sync(FULL, bandflags, 0, LPS);
     const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
     const bool go = live && !info.bad && info.mode != M_STORED && !rle;
     if (live && !go && sl == 0) a.status[tile] = info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
@@ -454,7 +476,6 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
         return v;
     };
 
-    /* per band running state; does any band need the core band added, or the quanta multiplied, at the flush */
     for (uint32_t c = sl; c < bands; c += LPS) { prev[c] = 0; pcf[c] = 0; rb[c] = 0; }
     uint4 *ring4 = reinterpret_cast<uint4 *>(ring);
     ring4[sl] = load_chunk(sl);
@@ -462,15 +483,17 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
     uint4 pend = load_chunk(2 * LPS + sl);
     uint32_t curhalf = 0;
     __syncwarp();
-    uint32_t derived = 0;
-    if (go) for (uint32_t c = sl; c < bands; c += LPS) derived |= cb[c] != c;
-#pragma unroll
-    for (int d = 1; d < LPS; d <<= 1) derived |= __shfl_xor_sync(FULL, derived, d, LPS);
+
     const uint64_t quanta = info.quanta;
-    const bool fix = go && (derived || quanta > 1), is_signed = a.dtype & 1;
+    const bool is_signed = a.dtype & 1;
+    const bool add_inline = go && staged && bandflags == 1;        /* the usual case: core bands are not derived */
+    const bool fix_bands = go && staged && (bandflags & 2);        /* chained band maps: the reference's sweep, at the flush */
+    const bool fix = go && staged && ((bandflags & 2) || quanta > 1);
+    const bool any_step = __any_sync(FULL, go && info.mode != M_FTL);
+    const bool any_fix = __any_sync(FULL, fix); /* warp uniform: the branches below contain warp barriers */
 
     WalkBits s;
-    s.open(ring, RW - 1, mis);
+    s.open((uint32_t)__cvta_generic_to_shared(ring), RW - 1, mis);
 
     const uint64_t order = info.order ? info.order : HILBERT;
     const bool ftl = info.mode == M_FTL;
@@ -486,6 +509,7 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
     T *out = reinterpret_cast<T *>(a.dst + (uint64_t)(live ? tile : 0) * a.dst_pitch);
 
     bool failed = false;
+    uint32_t upkeep = 1;
     for (uint32_t by = 0; by < nby; by++) {
         const uint32_t y0 = min(4 * by, a.h - 4);
         for (uint32_t gb = 0; gb < nbx; gb += sblocks) {
@@ -494,18 +518,21 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
             for (uint32_t bx = gb; bx < gend; bx++) {
                 const uint32_t x0 = min(4 * bx, a.w - 4);
                 for (uint32_t c = 0; c < bands; c++) {
-                    /* ring upkeep: on entering a half, the chunks held back in registers replace the half just left
-                       and the loads for the half after that start */
-                    const uint32_t hnow = s.k / HW;
-                    if (hnow != curhalf) {
-                        curhalf = hnow;
-                        __syncwarp(submask);
-                        ring4[((hnow + 1) & 1) * LPS + sl] = pend;
-                        pend = load_chunk((hnow + 2) * LPS + sl);
-                        __syncwarp(submask);
+                    /* ring upkeep every few groups: on entering a half, the chunks held back in registers replace the
+                       half just left and the loads for the half after that start */
+                    if (--upkeep == 0) {
+                        upkeep = UPKEEP;
+                        const uint32_t hnow = s.k / HW;
+                        if (hnow != curhalf) {
+                            curhalf = hnow;
+                            __syncwarp(submask);
+                            ring4[((hnow + 1) & 1) * LPS + sl] = pend;
+                            pend = load_chunk((hnow + 2) * LPS + sl);
+                            __syncwarp(submask);
+                        }
                     }
                     const W pv = prev[c];
-                    const uint32_t oldrung = rb[c];
+                    const uint32_t oldrung = rb[c], kc = cb[c], hc = head[c];
 
                     s.refill();
                     const uint32_t x = (uint32_t)s.buf;
@@ -514,8 +541,10 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
                     s.advance((x & 1) ? cs >> 12 : 1);
 
                     W v[VPL];
+                    uint32_t r = 0;
+                    bool want_step = false;
                     if (ftl || (cs & 0xfff) != 0 || cs == 0) {
-                        const uint32_t r = (oldrung + cs) & UMASK;
+                        r = (oldrung + cs) & UMASK;
                         rb[c] = (uint8_t)r;
                         if (r == 0) { /* flag, then 16 raw bits (reference: QB3decode.h:148-160) */
                             s.refill();
@@ -529,14 +558,25 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
                             uint32_t code[VPL];
 #pragma unroll
                             for (int j = 0; j < VPL; j++) code[j] = 0;
-                            const bool every = BITS == 16 && r == 15; /* two 17 bit codes exceed what one refill promises */
+                            if (BITS == 16 && r == 15) { /* two 17 bit codes exceed what one refill promises */
 #pragma unroll
-                            for (int i = 0; i < 16; i++) {
-                                if (i % VPR == 0 || every) s.refill();
-                                const uint32_t lo = (uint32_t)s.buf;
-                                const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
-                                if (sl == i / VPL) code[i % VPL] = lo;
-                                s.advance(r + b0 + t);
+                                for (int i = 0; i < 16; i++) {
+                                    s.refill();
+                                    const uint32_t lo = (uint32_t)s.buf;
+                                    const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
+                                    if (sl == i / VPL) code[i % VPL] = lo;
+                                    s.advance(r + b0 + t);
+                                }
+                            }
+                            else {
+#pragma unroll
+                                for (int i = 0; i < 16; i++) {
+                                    if (i % VPR == 0) s.refill();
+                                    const uint32_t lo = (uint32_t)s.buf;
+                                    const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
+                                    if (sl == i / VPL) code[i % VPL] = lo;
+                                    s.advance(r + b0 + t);
+                                }
                             }
                             const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
 #pragma unroll
@@ -546,35 +586,38 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
                                 if (val - fm1 <= 1u) val ^= sm; /* middle swap at rungs 1..7 */
                                 v[j] = val;
                             }
-                            if (!ftl) { /* step undo (reference: QB3decode.h:285-289); value i lives in lane i / VPL, slot i % VPL */
-                                uint32_t kk = 0, ok = 1, m[VPL];
-#pragma unroll
-                                for (int j = 0; j < VPL; j++) {
-                                    m[j] = (__ballot_sync(submask, (v[j] >> r) & 1) >> (sub * LPS)) & (LPS == 32 ? FULL : (1u << LPS) - 1);
-                                    kk += __popc(m[j]);
-                                }
-#pragma unroll
-                                for (int j = 0; j < VPL; j++) ok &= m[j] == (1u << ((kk + VPL - 1 - j) / VPL)) - 1;
-                                if (ok && kk < 16) {
-#pragma unroll
-                                    for (int j = 0; j < VPL; j++) if (sl * VPL + j == kk) v[j] ^= 1u << r;
-                                }
-                            }
+                            want_step = !ftl;
                         }
                     }
                     else { /* common factor or index group: every lane parses it, then keeps its own values */
                         W sg[16];
                         uint8_t rbv = (uint8_t)oldrung;
                         W pc = pcf[c];
-                        failed |= read_special_group<W, BITS, U>(s, sg, rbv, pc);
+                        WalkBits t = s; /* a copy: the reader itself must never have its address taken, it lives in registers */
+                        failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
+                        s = t;
                         rb[c] = rbv;
                         pcf[c] = pc;
 #pragma unroll
                         for (int j = 0; j < VPL; j++) {
-                            W t = 0;
+                            W t2 = 0;
 #pragma unroll
-                            for (int i = 0; i < 16; i++) if (sl * VPL + j == i) t = sg[i];
-                            v[j] = t;
+                            for (int i = 0; i < 16; i++) if (sl * VPL + j == i) t2 = sg[i];
+                            v[j] = t2;
+                        }
+                    }
+                    if (any_step) { /* step undo (reference: QB3decode.h:285-289); value i lives in lane i / VPL, slot i % VPL */
+                        uint32_t kk = 0, ok = 1, m[VPL];
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) {
+                            m[j] = (__ballot_sync(FULL, want_step && ((v[j] >> r) & 1)) >> (sub * LPS)) & (LPS == 32 ? FULL : (1u << LPS) - 1);
+                            kk += __popc(m[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) ok &= m[j] == (1u << ((kk + VPL - 1 - j) / VPL)) - 1;
+                        if (want_step && ok && kk < 16) {
+#pragma unroll
+                            for (int j = 0; j < VPL; j++) if (sl * VPL + j == kk) v[j] ^= 1u << r;
                         }
                     }
 
@@ -585,27 +628,41 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
                     W inc = tot;
 #pragma unroll
                     for (int d = 1; d < LPS; d <<= 1) {
-                        const W o = __shfl_up_sync(submask, inc, d, LPS);
+                        const W o = __shfl_up_sync(FULL, inc, d, LPS);
                         if (sl >= d) inc += o;
                     }
                     const W base = pv + inc - tot;
-                    prev[c] = (pv + __shfl_sync(submask, inc, LPS - 1, LPS)) & TM;
-                    T *dstp = staged ? stage + (size_t)(x0 - xs) * bands + c
-                                     : out + (uint64_t)y0 * a.stride + (uint64_t)x0 * bands + c;
-                    if (staged || go) {
+                    prev[c] = (pv + __shfl_sync(FULL, inc, LPS - 1, LPS)) & TM;
+                    if (staged) {
+                        T *p = stage + (size_t)(x0 - xs) * bands + c;
+                        if (add_inline) {
+                            for (uint32_t e = hc; e != NONE; e = nextc[e]) { /* derived bands staged before this, their core band */
 #pragma unroll
-                        for (int j = 0; j < VPL; j++) dstp[off[j]] = (T)((base + acc[j]) & TM);
+                                for (int j = 0; j < VPL; j++) p[off[j] + e - c] = (T)(p[off[j] + e - c] + base + acc[j]);
+                            }
+                            if (kc < c) { /* derived from a band that is already staged */
+#pragma unroll
+                                for (int j = 0; j < VPL; j++) acc[j] += p[off[j] + kc - c];
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) p[off[j]] = (T)(base + acc[j]);
+                    }
+                    else if (go) {
+                        T *p = out + (uint64_t)y0 * a.stride + (uint64_t)x0 * bands + c;
+#pragma unroll
+                        for (int j = 0; j < VPL; j++) p[off[j]] = (T)(base + acc[j]);
                     }
                 }
             }
             if (!staged) continue;
             __syncwarp();
             const uint32_t npx = xe - xs;
-            if (fix) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
-                for (uint32_t r = 0; r < 4; r++)
+            if (any_fix) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
+                for (uint32_t r = 0; fix && r < 4; r++)
                     for (uint32_t px = sl; px < npx; px += LPS) {
                         T *p = stage + (size_t)r * rowelems + (size_t)px * bands;
-                        if (derived)
+                        if (fix_bands)
                             for (uint32_t c = 0; c < bands; c++) {
                                 const uint32_t k = cb[c];
                                 if (k != c) p[c] = (T)(p[c] + p[k]);
@@ -638,7 +695,8 @@ __global__ void __launch_bounds__(32) walk_kernel(const DecArgs a, const uint32_
     if (go && sl == 0) {
         const uint64_t total = 8 * plen, used = s.consumed();
         const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
-        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : (!staged && fix) ? ST_FINISH : (uint32_t)QB3CU_TILE_OK;
+        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT
+                             : (!staged && (bandflags || quanta > 1)) ? ST_FINISH : (uint32_t)QB3CU_TILE_OK;
     }
 }
 
@@ -838,7 +896,7 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaS
             const uint32_t nbx = (a.w + 3) / 4;
             if (stage_blocks > ((nbx + 3) & ~3u)) stage_blocks = (nbx + 3) & ~3u;
         }
-        const uint32_t stage_off = (hw_bytes + a.bands * 10 + 15) & ~15u;
+        const uint32_t stage_off = (hw_bytes + a.bands * 12 + 15) & ~15u;
         const uint32_t sstride = stage_off + stage_blocks * block_bytes + 16; /* the spare vector shifts the streams' banks */
         err = lps == 4 ? launch_walk<T, 4>(a, stage_blocks, stage_off, sstride, st)
             : lps == 8 ? launch_walk<T, 8>(a, stage_blocks, stage_off, sstride, st)

@@ -700,6 +700,505 @@ __global__ void __launch_bounds__(32, 16) walk_kernel(const DecArgs a, const uin
     }
 }
 
+/* ------------------------------------------------------------------ two pass decode: scan, then rebuild */
+
+constexpr uint32_t ST_PARSED = 0x20000000u; /* scan_kernel has written the tile's group records, rebuild_kernel is due */
+
+/*
+ * Bit buffer of scan_kernel: one stream per lane. 64 bits of look-ahead in registers, fed a 32 bit word at a time from
+ * the lane's ring of 16 byte chunks in shared memory (chunk slot s of lane l at ring + (s * 32 + l) * 16), one word of
+ * read-ahead. The ring itself is filled by cp.async, several chunks ahead, so neither global nor shared memory latency
+ * is on the parse chain. The refill is a select, not a branch: the lanes of a warp must stay together.
+ */
+template <int SLOTS> struct ScanBits {
+    uint64_t buf;
+    uint32_t ring;  /* shared memory address of slot 0 of this lane */
+    uint32_t nb, nxt, k, w0, sh;
+
+    __device__ __forceinline__ uint32_t word(uint32_t w) const
+    {
+        return lds32(ring + ((w >> 2) & (SLOTS - 1)) * 512 + (w & 3) * 4);
+    }
+    __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t mis)
+    {
+        ring = ring_addr;
+        w0 = mis >> 2; sh = 8 * (mis & 3);
+        buf = (uint64_t)(word(w0) >> sh);
+        nb = 32 - sh;
+        buf |= (uint64_t)word(w0 + 1) << nb;
+        nb += 32;
+        nxt = word(w0 + 2);
+        k = w0 + 3;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        const bool take = nb <= 32;
+        const uint32_t cand = word(k); /* always loaded, kept only when the word before it moves into the buffer */
+        buf |= (uint64_t)(take ? nxt : 0u) << (nb & 63);
+        nb += take ? 32u : 0u;
+        nxt = take ? cand : nxt;
+        k += take ? 1u : 0u;
+    }
+    __device__ __forceinline__ uint64_t peek() { refill(); return buf; }
+    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; } /* n <= 33, after peek() / refill() */
+    __device__ __forceinline__ uint64_t get(uint32_t n)
+    {
+        refill();
+        const uint64_t v = buf & lowmask64(n);
+        advance(n);
+        return v;
+    }
+    __device__ __forceinline__ uint64_t consumed() const { return 32ull * (k - 1 - w0) - sh - nb; }
+};
+
+/* 16 bytes global -> shared, the tail beyond nbytes zero filled; predicated so that the warp does not branch */
+__device__ __forceinline__ void cp_async16_zfill(bool pred, uint32_t smem_addr, const void *gmem, uint32_t nbytes)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p cp.async.ca.shared.global [%1], [%2], 16, %3;\n\t}"
+                 :: "r"((uint32_t)pred), "r"(smem_addr), "l"(gmem), "r"(nbytes) : "memory");
+}
+
+/*
+ * Pass one, 8 and 16 bit types: the serial part of decoding and nothing else. One stream per lane walks its groups and
+ * only works out where each one starts and which rung its band is at afterwards: a 32 bit record per group,
+ * (start bit << 4) | rung. Values are not decoded (common factor groups excepted: their next rung depends on the
+ * values, QB3decode.h:664), nothing is reconstructed or stored, so the latency bound chain of a stream is as short
+ * as it gets: per value an AND, an add and a funnel shift. rebuild_kernel then decodes all groups of a tile in parallel.
+ */
+template <typename T>
+__global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups)
+{
+    typedef uint32_t W;
+    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
+    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
+    constexpr int VPR = BITS == 8 ? 3 : 2;      /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
+    constexpr int SLOTS = BITS == 8 ? 16 : 32, AHEAD = SLOTS - 4; /* ring chunks per lane; chunks requested ahead of the parse position */
+    constexpr int PERGROUP = BITS == 8 ? 2 : 3; /* chunks one group can consume (6 and 12 words) */
+    constexpr int NTW = (2 << U) / 8;           /* 32 bit words of a 4 bit per entry switch table */
+
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x, bands = a.bands;
+    uint8_t *rb = smem + SLOTS * 512;                               /* [band][lane] running rung */
+    uint32_t *pcf = reinterpret_cast<uint32_t *>(rb + 32 * bands);  /* [band][lane] last common factor */
+    uint8_t *cbs = reinterpret_cast<uint8_t *>(pcf + 32 * bands);   /* [band][lane] band map, header parsing only */
+
+    /* rung switch decode (QB3decode.h:98-116) as two 4 bit per entry tables in registers: length, delta */
+    uint32_t tlen[NTW], tdel[NTW];
+#pragma unroll
+    for (int w = 0; w < NTW; w++) {
+        tlen[w] = tdel[w] = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const uint32_t d = ds_entry(U, 8 * w + e);
+            tlen[w] |= (d >> 12) << (4 * e);
+            tdel[w] |= (d & 15) << (4 * e);
+        }
+    }
+
+    const uint32_t tile = blockIdx.x * 32 + lane;
+    const bool live = tile < a.ntiles;
+    const uint8_t *stream = nullptr;
+    uint64_t slen = 0;
+    StreamInfo info;
+    info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
+    if (live) {
+        stream = a.streams + a.offsets[tile];
+        slen = a.lens[tile];
+        parse_header(stream, slen, a, info, cbs + lane, 32);
+    }
+    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
+    const bool go = live && !info.bad && info.mode != M_STORED && !rle;
+    if (live && !go) a.status[tile] = info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
+
+    const uint8_t *payload = go ? stream + info.data_off : nullptr;
+    const uint64_t plen = go ? slen - info.data_off : 0;
+    const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
+    const uint8_t *abase = go ? payload - mis : a.streams;
+    const uint64_t span = go ? mis + plen : 0;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + lane * 16;
+    uint32_t issued = 0; /* chunks requested so far */
+    auto request = [&](bool pred) {
+        const uint64_t start = 16ull * issued;
+        const uint32_t nbytes = start >= span ? 0u : (uint32_t)min((uint64_t)16, span - start);
+        cp_async16_zfill(pred, ring + (issued & (SLOTS - 1)) * 512, abase + (nbytes ? start : 0), nbytes);
+        issued += pred ? 1u : 0u;
+    };
+    for (int i = 0; i < AHEAD; i++) request(true);
+    cp_async_commit();
+    cp_async_wait<0>();
+    for (uint32_t c = 0; c < bands; c++) { rb[c * 32 + lane] = 0; pcf[c * 32 + lane] = 0; }
+    __syncwarp();
+
+    ScanBits<SLOTS> s;
+    s.open(ring, mis);
+    const bool ftl = info.mode == M_FTL;
+    uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
+
+    bool failed = false;
+    uint32_t c = 0;
+    for (uint32_t g = 0; g < ngroups; g++) {
+        /* ring upkeep: keep AHEAD chunks requested beyond the one being read; what was asked for two groups ago has landed */
+#pragma unroll
+        for (int i = 0; i < PERGROUP; i++) request(issued < (s.k >> 2) + AHEAD);
+        cp_async_commit();
+        cp_async_wait<2>();
+
+        const uint32_t oldrung = rb[c * 32 + lane];
+        const uint32_t pos = (uint32_t)s.consumed();
+        s.refill();
+        const uint32_t x = (uint32_t)s.buf;
+        const uint32_t idx = (x >> 1) & LMASK;
+        uint32_t wl = tlen[0], wd = tdel[0];
+#pragma unroll
+        for (int w = 1; w < NTW; w++) if ((idx >> 3) == (uint32_t)w) { wl = tlen[w]; wd = tdel[w]; }
+        const uint32_t sft = 4 * (idx & 7);
+        const uint32_t slen_ = (x & 1) ? (wl >> sft) & 15 : 1, delta = (x & 1) ? (wd >> sft) & 15 : 0;
+        s.advance(slen_);
+        uint32_t r;
+        if (ftl || delta != 0 || slen_ == 1) {
+            r = (oldrung + delta) & UMASK;
+            /* rung 0 walks the same sixteen steps with every length forced to zero, then takes its flag and raw bits */
+            const uint32_t live_mask = r ? 1u : 0u;
+            if (BITS == 16 && r == 15) { /* two 17 bit codes exceed what one refill promises; rare */
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    s.refill();
+                    const uint32_t lo = (uint32_t)s.buf;
+                    const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
+                    s.advance(r + b0 + t);
+                }
+            }
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (i % VPR == 0) s.refill();
+                    const uint32_t lo = (uint32_t)s.buf;
+                    const uint32_t b0 = lo & live_mask, t = b0 & (lo >> 1);
+                    s.advance(r + b0 + t);
+                }
+            }
+            s.refill();
+            s.advance(r ? 0u : (((uint32_t)s.buf & 1) ? 17u : 1u)); /* reference: QB3decode.h:148-160 */
+        }
+        else { /* common factor or index group: parsed in full, it is rare */
+            W sg[16];
+            uint8_t rbv = (uint8_t)oldrung;
+            W pc = pcf[c * 32 + lane];
+            ScanBits<SLOTS> t = s; /* a copy: the reader itself must never have its address taken, it lives in registers */
+            failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
+            s = t;
+            pcf[c * 32 + lane] = pc;
+            r = rbv;
+        }
+        rb[c * 32 + lane] = (uint8_t)r;
+        if (go) rec[g] = (pos << 4) | r;
+        c = c + 1 == bands ? 0 : c + 1;
+    }
+    cp_async_wait<0>();
+    if (go) {
+        const uint64_t total = 8 * plen, used = s.consumed();
+        const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
+        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : ST_PARSED;
+    }
+}
+
+/* Bit reader of rebuild_kernel: a thread reads one group at a known bit position straight from global memory
+   (neighbouring threads read neighbouring words). Same contract as the others: 33 valid bits after refill(), zeros
+   past the end of the payload. */
+struct GroupBits {
+    const uint32_t *base; /* 4 byte aligned, at or before the payload */
+    uint64_t buf;
+    uint32_t nb, k, nwords, tailmask;
+
+    __device__ __forceinline__ uint32_t load(uint32_t i) const
+    {
+        uint32_t w = i < nwords ? __ldg(base + i) : 0u;
+        if (i + 1 == nwords) w &= tailmask;
+        return w;
+    }
+    /* bit is counted from the payload's first byte, which sits mis bytes after base */
+    __device__ __forceinline__ void open(const uint8_t *payload, uint64_t plen, uint64_t bit)
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)payload & 3);
+        const uint64_t span = mis + plen;
+        const uint32_t tail = (uint32_t)span & 3;
+        base = reinterpret_cast<const uint32_t *>(payload - mis);
+        nwords = (uint32_t)((span + 3) >> 2);
+        tailmask = tail ? (1u << (8 * tail)) - 1 : 0xffffffffu;
+        const uint64_t abs = bit + 8 * mis;
+        k = (uint32_t)(abs >> 5);
+        const uint32_t sh = (uint32_t)abs & 31;
+        buf = (uint64_t)(load(k) >> sh);
+        nb = 32 - sh;
+        buf |= (uint64_t)load(k + 1) << nb;
+        nb += 32;
+        k += 2;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (nb <= 32) {
+            buf |= (uint64_t)load(k) << nb;
+            nb += 32;
+            k++;
+        }
+    }
+    __device__ __forceinline__ uint64_t peek() { refill(); return buf; }
+    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; }
+    __device__ __forceinline__ uint64_t get(uint32_t n)
+    {
+        refill();
+        const uint64_t v = buf & lowmask64(n);
+        advance(n);
+        return v;
+    }
+};
+
+/*
+ * Per band scan over the threads of a segment, thread t = block * bands + band: warp w takes bands w, w + nwarps, ...
+ * and runs along the band's blocks 32 at a time. ADD: exclusive prefix sum of val, seeded and continued by carry[band].
+ * LAST: the val of the latest earlier thread of the band with flag set, else carry[band]; carry moves on likewise.
+ * val_s / flag_s are shared arrays indexed by thread; results replace val_s. Call with all threads, between barriers.
+ */
+template <bool LAST>
+__device__ __forceinline__ void band_scan(uint32_t *val_s, const uint8_t *flag_s, uint32_t *carry, uint32_t nblk, uint32_t bands)
+{
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t c = warp; c < bands; c += nwarps) {
+        uint32_t run = carry[c];
+        for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
+            const uint32_t b = b0 + lane, t = b * bands + c;
+            const bool in = b < nblk;
+            uint32_t v = in ? val_s[t] : 0u;
+            if (!LAST) {
+                uint32_t inc = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                if (in) val_s[t] = run + inc - v;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            else {
+                uint32_t f = in && flag_s[t] ? 1u : 0u;
+                const uint32_t own_v = v, own_f = f;
+                /* inclusive "last flagged" scan */
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t ov = __shfl_up_sync(0xffffffffu, v, d), of = __shfl_up_sync(0xffffffffu, f, d);
+                    if (lane >= d && !f) { v = ov; f = of; }
+                }
+                /* exclusive: what the previous lane ended with */
+                uint32_t pv = __shfl_up_sync(0xffffffffu, v, 1), pf = __shfl_up_sync(0xffffffffu, f, 1);
+                if (lane == 0) pf = 0;
+                if (in) val_s[t] = pf ? pv : run;
+                const uint32_t lv = __shfl_sync(0xffffffffu, v, 31), lf = __shfl_sync(0xffffffffu, f, 31);
+                if (lf) run = lv;
+                (void)own_v; (void)own_f;
+            }
+        }
+        if (lane == 0) carry[c] = run;
+    }
+}
+
+/*
+ * Pass two, 8 and 16 bit types: with every group's start bit and rung known (scan_kernel), a tile decodes in parallel.
+ * One CTA per tile walks it a segment (a run of blocks of one block row, all bands) at a time, one thread per group:
+ *   1. the thread parses its group at its recorded position: values, step undo, sign unfolding, and the running sum
+ *      inside the group (QB3decode.h:603-722 for one group)
+ *   2. a per band scan of the group totals, seeded by the band's running value, gives every group its predecessor
+ *      (the decoder's prv, QB3decode.h:717-722); common factor groups that reuse the band's factor get it from a
+ *      "last written" scan of the same shape
+ *   3. pixels are scattered into four staged rows in shared memory; there the core band is added to the derived
+ *      bands (QB3decode.h:730-737) and quanta multiplied (QB3decode.cpp:77-107), and the rows leave as 16 byte vectors
+ */
+template <typename T>
+__global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups,
+                                                      const uint32_t seg_blocks, const uint32_t segs, const uint32_t rowpitch)
+{
+    typedef uint32_t W;
+    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
+    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
+    constexpr W TM = (W)((1ull << BITS) - 1);
+
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, NT = blockDim.x, tile = blockIdx.x, bands = a.bands;
+    uint8_t *stage = smem;                                                  /* [4][rowpitch] */
+    uint32_t *val_s = reinterpret_cast<uint32_t *>(stage + 4 * rowpitch);   /* [NT] */
+    uint32_t *carry_prev = val_s + NT;                                      /* [bands] */
+    uint32_t *carry_pcf = carry_prev + bands;                               /* [bands] */
+    uint8_t *flag_s = reinterpret_cast<uint8_t *>(carry_pcf + bands);       /* [NT] */
+    uint8_t *cb = flag_s + NT;                                              /* [bands] */
+    __shared__ StreamInfo info;
+    __shared__ uint32_t derived;
+
+    if (a.status[tile] != ST_PARSED) return;
+    const uint8_t *stream = a.streams + a.offsets[tile];
+    const uint64_t slen = a.lens[tile];
+    if (tid == 0) {
+        parse_header(stream, slen, a, info, cb, 1);
+        uint32_t d = 0;
+        for (uint32_t c = 0; c < bands; c++) d |= cb[c] != c;
+        derived = d;
+    }
+    for (uint32_t c = tid; c < bands; c += NT) { carry_prev[c] = 0; carry_pcf[c] = 0; }
+    __syncthreads();
+    const uint8_t *payload = stream + info.data_off;
+    const uint64_t plen = slen - info.data_off;
+    const uint64_t order = info.order ? info.order : HILBERT, quanta = info.quanta;
+    const bool ftl = info.mode == M_FTL, is_signed = a.dtype & 1;
+    const uint32_t *rec = recs + (size_t)tile * ngroups;
+    T *out = reinterpret_cast<T *>(a.dst + (uint64_t)tile * a.dst_pitch);
+    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4;
+    const uint32_t blk = tid / bands, c = tid - blk * bands;
+    const uint32_t rowelems = rowpitch / (uint32_t)sizeof(T);
+
+    for (uint32_t by = 0; by < nby; by++) {
+        const uint32_t y0 = min(4 * by, a.h - 4);
+        for (uint32_t sg = 0; sg < segs; sg++) {
+            const uint32_t bx0 = sg * seg_blocks, nblk = min(seg_blocks, nbx - bx0), ng = nblk * bands;
+            const uint32_t xs = min(4 * bx0, a.w - 4), xe = min(4 * (bx0 + nblk), a.w);
+            const bool active = tid < ng;
+            const uint32_t g = (by * nbx + bx0) * bands + tid;
+
+            W v[16];
+            uint32_t tot = 0;
+            uint32_t kind = 0; /* 1: common factor group that reuses the band's factor, 2: one that wrote a new factor */
+            uint32_t oldrung = 0, pos = 0;
+            if (active) {
+                pos = rec[g] >> 4;
+                oldrung = g >= bands ? rec[g - bands] & 15 : 0;
+                GroupBits s;
+                s.open(payload, plen, pos);
+                uint32_t cs = 0;
+                if (s.get(1)) {
+                    cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
+                    s.advance((cs >> 12) - 1);
+                }
+                if (ftl || (cs & 0xfff) != 0 || cs == 0) {
+                    const uint32_t r = (oldrung + cs) & UMASK;
+                    if (r == 0) {
+                        s.refill();
+                        const uint32_t y = (uint32_t)s.buf;
+                        const uint32_t b = (y & 1) ? (y >> 1) & 0xffffu : 0u;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = (b >> i) & 1;
+                    }
+                    else {
+                        const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
+                        uint32_t M = 0;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            s.refill();
+                            const uint32_t x = (uint32_t)s.buf;
+                            const uint32_t b0 = x & 1, t = b0 & (x >> 1), ht = half << t;
+                            uint32_t val = ((x >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
+                            s.advance(r + b0 + t);
+                            if (val - fm1 <= 1u) val ^= sm; /* middle swap at rungs 1..7 */
+                            v[i] = val;
+                            M |= ((val >> r) & 1u) << i;
+                        }
+                        if (!ftl) {
+                            const int k = step_decode_index(M);
+#pragma unroll
+                            for (int i = 0; i < 16; i++) if (i == k) v[i] ^= 1u << r;
+                        }
+                    }
+                }
+                else { /* common factor or index group; a reused factor is not known yet: parse with 0, redo below */
+                    GroupBits t = s;
+                    uint8_t rbv = (uint8_t)oldrung;
+                    W pc = 0xffffffffu;
+                    W sgv[16]; /* the out-of-line parser takes an array by reference: keep that one out of v's registers */
+                    read_special_group<W, BITS, U>(t, sgv, rbv, pc);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = sgv[i];
+                    /* what kind it was: the flag after the signal and the switch (QB3decode.h:624-640) */
+                    GroupBits p = s;
+                    const uint32_t e = ds_entry(U, (uint32_t)p.peek() & LMASK);
+                    p.advance((e >> 12) - 1);
+                    if (((oldrung + e) & UMASK) != UMASK) kind = p.get(1) ? 2 : 1;
+                    if (kind == 2) tot = pc; /* the factor this group wrote, for the scan */
+                }
+            }
+            /* bands' factors: only when a common factor group is around */
+            if (__syncthreads_or(kind != 0)) {
+                val_s[tid] = tot;
+                flag_s[tid] = kind == 2;
+                __syncthreads();
+                band_scan<true>(val_s, flag_s, carry_pcf, nblk, bands);
+                __syncthreads();
+                if (kind == 1) {
+                    GroupBits s;
+                    s.open(payload, plen, pos);
+                    s.advance(1 + (cs_signal(U) >> 12) - 1);
+                    uint8_t rbv = (uint8_t)oldrung;
+                    W pc = val_s[tid];
+                    W sgv[16];
+                    read_special_group<W, BITS, U>(s, sgv, rbv, pc);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = sgv[i];
+                }
+                __syncthreads();
+            }
+            /* running sum inside the group, then across the band's groups */
+            tot = 0;
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) { tot += smag<BITS, W>(v[i]); v[i] = tot; }
+            }
+            val_s[tid] = tot;
+            __syncthreads();
+            band_scan<false>(val_s, nullptr, carry_prev, nblk, bands);
+            __syncthreads();
+            if (active) {
+                const uint32_t base = val_s[tid];
+                const uint32_t x0 = min(4 * (bx0 + blk), a.w - 4);
+                T *p = reinterpret_cast<T *>(stage) + (size_t)(x0 - xs) * bands + c;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t n = (uint32_t)(order >> (4 * (15 - i))) & 15;
+                    p[(n >> 2) * rowelems + (n & 3) * bands] = (T)(base + v[i]);
+                }
+            }
+            __syncthreads();
+            const uint32_t npx = xe - xs;
+            if (derived || quanta > 1) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
+                for (uint32_t i = tid; i < 4 * npx; i += NT) {
+                    const uint32_t r = i / npx, px = i - r * npx;
+                    T *p = reinterpret_cast<T *>(stage) + (size_t)r * rowelems + (size_t)px * bands;
+                    if (derived)
+                        for (uint32_t k = 0; k < bands; k++) {
+                            const uint32_t kc = cb[k];
+                            if (kc != k) p[k] = (T)(p[k] + p[kc]);
+                        }
+                    if (quanta > 1)
+                        for (uint32_t k = 0; k < bands; k++)
+                            p[k] = (T)dequantize_value<BITS>((uint64_t)p[k], quanta, is_signed);
+                }
+                __syncthreads();
+            }
+            /* staged rows leave as the widest vectors the destination allows */
+            const uint32_t rowbytes = npx * bands * (uint32_t)sizeof(T);
+            for (uint32_t r = 0; r < 4; r++) {
+                uint8_t *gp = reinterpret_cast<uint8_t *>(out + (uint64_t)(y0 + r) * a.stride + (uint64_t)xs * bands);
+                const uint8_t *sp = stage + r * rowpitch;
+                if ((((uintptr_t)gp | rowbytes) & 15) == 0)
+                    for (uint32_t j = 16 * tid; j < rowbytes; j += 16 * NT)
+                        st_stream16(gp + j, *reinterpret_cast<const uint4 *>(sp + j));
+                else if ((((uintptr_t)gp | rowbytes) & 3) == 0)
+                    for (uint32_t j = 4 * tid; j < rowbytes; j += 4 * NT)
+                        *reinterpret_cast<uint32_t *>(gp + j) = *reinterpret_cast<const uint32_t *>(sp + j);
+                else
+                    for (uint32_t j = sizeof(T) * tid; j < rowbytes; j += sizeof(T) * NT)
+                        *reinterpret_cast<T *>(gp + j) = *reinterpret_cast<const T *>(sp + j);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) a.status[tile] = QB3CU_TILE_OK;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, const bool only_deferred)
 {
@@ -875,6 +1374,68 @@ static cudaError_t launch_walk(const DecArgs &a, uint32_t stage_blocks, uint32_t
     return cudaGetLastError();
 }
 
+static int decode_path_override() /* QB3CU_DECODE=walk forces the single kernel path */
+{
+    static const int v = [] { const char *e = getenv("QB3CU_DECODE"); return e && e[0] == 'w' ? 1 : 0; }();
+    return v;
+}
+
+template <typename T> static cudaError_t launch_walk_any(const DecArgs &a, cudaStream_t st)
+{
+    /* lanes per stream: the fewer streams there are, the more lanes each one can have for its parallel part */
+    int lps = walk_lanes_override();
+    if (lps != 4 && lps != 8 && lps != 16) lps = a.ntiles >= 2048 ? 8 : 16;
+    const uint32_t hw_bytes = 2 * 16 * (uint32_t)lps;
+    /* staged run of blocks: a multiple of four (rows stay 16 byte multiples) within 8 KB per stream, aiming at 2 KB */
+    const uint32_t block_bytes = 16 * a.bands * (uint32_t)sizeof(T);
+    uint32_t stage_blocks = 0;
+    if (4 * block_bytes <= 8192) {
+        stage_blocks = 4 * (2048 / (4 * block_bytes));
+        if (stage_blocks < 4) stage_blocks = 4;
+        const uint32_t nbx = (a.w + 3) / 4;
+        if (stage_blocks > ((nbx + 3) & ~3u)) stage_blocks = (nbx + 3) & ~3u;
+    }
+    const uint32_t stage_off = (hw_bytes + a.bands * 12 + 15) & ~15u;
+    const uint32_t sstride = stage_off + stage_blocks * block_bytes + 16; /* the spare vector shifts the streams' banks */
+    return lps == 4 ? launch_walk<T, 4>(a, stage_blocks, stage_off, sstride, st)
+         : lps == 8 ? launch_walk<T, 8>(a, stage_blocks, stage_off, sstride, st)
+                    : launch_walk<T, 16>(a, stage_blocks, stage_off, sstride, st);
+}
+
+/* scan_kernel + rebuild_kernel; the group records live in stream ordered scratch memory */
+template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, cudaStream_t st)
+{
+    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
+    uint32_t *recs = nullptr;
+    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&recs), (size_t)a.ntiles * ngroups * sizeof(uint32_t), st);
+    if (err != cudaSuccess) return err;
+    constexpr int SLOTS = sizeof(T) == 1 ? 16 : 32;
+    const size_t smem1 = (size_t)SLOTS * 512 + (size_t)32 * a.bands * 6;
+    err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (err == cudaSuccess) {
+        scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
+        uint32_t seg_blocks = 512 / a.bands;
+        if (seg_blocks > nbx) seg_blocks = nbx;
+        uint32_t segs = (nbx + seg_blocks - 1) / seg_blocks;
+        seg_blocks = (nbx + segs - 1) / segs;
+        segs = (nbx + seg_blocks - 1) / seg_blocks;
+        const uint32_t threads = (seg_blocks * a.bands + 31) & ~31u;
+        const uint32_t rowpitch = (seg_blocks * 4 * a.bands * (uint32_t)sizeof(T) + 15) & ~15u;
+        const size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * 5 + (size_t)a.bands * 9 + 16;
+        err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (err == cudaSuccess) {
+            rebuild_kernel<T><<<a.ntiles, threads, smem2, st>>>(a, recs, ngroups, seg_blocks, segs, rowpitch);
+            err = cudaGetLastError();
+        }
+    }
+    const cudaError_t ferr = cudaFreeAsync(recs, st);
+    return err != cudaSuccess ? err : ferr;
+}
+
 /* kernels launched, for the bookkeeping of qb3cu_kernel_launches */
 template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaStream_t st, uint32_t &launches)
 {
@@ -883,26 +1444,17 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaS
     bool walked = false;
     launches = 0;
     if constexpr (sizeof(T) <= 2) if (a.w >= 4 && a.h >= 4) {
-        /* lanes per stream: the fewer streams there are, the more lanes each one can have for its parallel part */
-        int lps = walk_lanes_override();
-        if (lps != 4 && lps != 8 && lps != 16) lps = a.ntiles >= 2048 ? 8 : 16;
-        const uint32_t hw_bytes = 2 * 16 * (uint32_t)lps;
-        /* staged run of blocks: a multiple of four (rows stay 16 byte multiples) within 8 KB per stream, aiming at 2 KB */
-        const uint32_t block_bytes = 16 * a.bands * (uint32_t)sizeof(T);
-        uint32_t stage_blocks = 0;
-        if (4 * block_bytes <= 8192) {
-            stage_blocks = 4 * (2048 / (4 * block_bytes));
-            if (stage_blocks < 4) stage_blocks = 4;
-            const uint32_t nbx = (a.w + 3) / 4;
-            if (stage_blocks > ((nbx + 3) & ~3u)) stage_blocks = (nbx + 3) & ~3u;
+        /* two passes when a group's start bit fits its record (28 bits), else the single kernel */
+        const uint64_t max_bits = 8 * (1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) + 1));
+        if (max_bits < (1ull << 28) && !decode_path_override()) {
+            err = launch_scan_rebuild<T>(a, st);
+            launches += 2;
         }
-        const uint32_t stage_off = (hw_bytes + a.bands * 12 + 15) & ~15u;
-        const uint32_t sstride = stage_off + stage_blocks * block_bytes + 16; /* the spare vector shifts the streams' banks */
-        err = lps == 4 ? launch_walk<T, 4>(a, stage_blocks, stage_off, sstride, st)
-            : lps == 8 ? launch_walk<T, 8>(a, stage_blocks, stage_off, sstride, st)
-                       : launch_walk<T, 16>(a, stage_blocks, stage_off, sstride, st);
+        else {
+            err = launch_walk_any<T>(a, st);
+            launches += 1;
+        }
         if (err != cudaSuccess) return err;
-        launches++;
         walked = true;
     }
     const size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);

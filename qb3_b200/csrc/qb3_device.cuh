@@ -86,6 +86,15 @@ __device__ __forceinline__ void st_stream16(void *p, uint4 v)
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+/* cp.async: 16 bytes global -> shared without passing through registers (LDGSTS) */
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 /* CTA wide exclusive scan of one uint32 per thread; returns the prefix, total gets the sum. blockDim.x <= 1024.
    scratch: 33 words of shared memory. Contains two __syncthreads(). */
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *scratch, uint32_t &total)

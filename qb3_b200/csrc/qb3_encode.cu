@@ -60,13 +60,6 @@ template <int BITS> __device__ __forceinline__ uint64_t quantize_value(uint64_t 
  * Fast path: 16 byte copies at the source's own alignment (row r lands at stage + r * rowpitch + (addr & 15)).
  * General path: element by element through the small-image reorder (QB3encode.cpp:351-389) and the quantiser.
  */
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 /* Issues the copies; whole 16 byte units travel as cp.async (LDGSTS, L2 only), so the rows of the next segment
    are in flight while the current one is being coded. The caller commits and waits. */

@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void band_scan(uint32_t *val_s, const uint8_t *flag_s
  *      bands (QB3decode.h:730-737) and quanta multiplied (QB3decode.cpp:77-107), and the rows leave as 16 byte vectors
  */
 template <typename T>
-__global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups,
+__global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups,
                                                       const uint32_t seg_blocks, const uint32_t segs, const uint32_t rowpitch)
 {
     typedef uint32_t W;
@@ -1030,7 +1030,9 @@ __global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const 
     uint8_t *flag_s = reinterpret_cast<uint8_t *>(carry_pcf + bands);       /* [NT] */
     uint8_t *cb = flag_s + NT;                                              /* [bands] */
     __shared__ StreamInfo info;
-    __shared__ uint32_t derived;
+    __shared__ uint32_t bandflags; /* 1: some band is derived, 2: a core band is itself derived (only hand made streams) */
+    __shared__ uint16_t dsw[2u << U]; /* rung switch decode table */
+    constexpr int VPR = BITS == 8 ? 3 : 2; /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
 
     if (a.status[tile] != ST_PARSED) return;
     const uint8_t *stream = a.streams + a.offsets[tile];
@@ -1038,11 +1040,19 @@ __global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const 
     if (tid == 0) {
         parse_header(stream, slen, a, info, cb, 1);
         uint32_t d = 0;
-        for (uint32_t c = 0; c < bands; c++) d |= cb[c] != c;
-        derived = d;
+        for (uint32_t c = 0; c < bands; c++) {
+            const uint32_t k = cb[c];
+            if (k != c) d |= 1 | (cb[k] != k ? 2 : 0);
+        }
+        bandflags = d;
     }
     for (uint32_t c = tid; c < bands; c += NT) { carry_prev[c] = 0; carry_pcf[c] = 0; }
+    for (uint32_t i = tid; i < (2u << U); i += NT) dsw[i] = (uint16_t)ds_entry(U, i);
     __syncthreads();
+    const bool derived = bandflags != 0;
+    /* the plain case adds the core band straight from the core band's thread's pixels; chained band maps and
+       quantised derived bands go through the reference's per pixel sweep instead */
+    const bool sweep = (bandflags & 2) || (derived && info.quanta > 1);
     const uint8_t *payload = stream + info.data_off;
     const uint64_t plen = slen - info.data_off;
     const uint64_t order = info.order ? info.order : HILBERT, quanta = info.quanta;
@@ -1052,6 +1062,13 @@ __global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const 
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4;
     const uint32_t blk = tid / bands, c = tid - blk * bands;
     const uint32_t rowelems = rowpitch / (uint32_t)sizeof(T);
+    const uint32_t core = cb[c < bands ? c : 0];
+    uint32_t poff[16]; /* where the 16 values of a block go in the staged rows */
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t n = (uint32_t)(order >> (4 * (15 - i))) & 15;
+        poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
+    }
 
     for (uint32_t by = 0; by < nby; by++) {
         const uint32_t y0 = min(4 * by, a.h - 4);
@@ -1071,9 +1088,10 @@ __global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const 
                 GroupBits s;
                 s.open(payload, plen, pos);
                 uint32_t cs = 0;
-                if (s.get(1)) {
-                    cs = ds_entry(U, (uint32_t)s.peek() & LMASK);
-                    s.advance((cs >> 12) - 1);
+                {
+                    const uint32_t x = (uint32_t)s.buf; /* open() left at least 33 bits */
+                    if (x & 1) cs = dsw[(x >> 1) & LMASK];
+                    s.advance((x & 1) ? cs >> 12 : 1);
                 }
                 if (ftl || (cs & 0xfff) != 0 || cs == 0) {
                     const uint32_t r = (oldrung + cs) & UMASK;
@@ -1086,10 +1104,11 @@ __global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const 
                     }
                     else {
                         const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
+                        const bool every = BITS == 16 && r == 15; /* two 17 bit codes exceed what one refill promises */
                         uint32_t M = 0;
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            s.refill();
+                            if (i % VPR == 0 || every) s.refill();
                             const uint32_t x = (uint32_t)s.buf;
                             const uint32_t b0 = x & 1, t = b0 & (x >> 1), ht = half << t;
                             uint32_t val = ((x >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
@@ -1151,33 +1170,51 @@ __global__ void __launch_bounds__(512, 1) rebuild_kernel(const DecArgs a, const 
             __syncthreads();
             band_scan<false>(val_s, nullptr, carry_prev, nblk, bands);
             __syncthreads();
+            const uint32_t npx = xe - xs;
+            T *p = reinterpret_cast<T *>(stage) + (size_t)(min(4 * (bx0 + blk), a.w - 4) - xs) * bands + c;
             if (active) {
                 const uint32_t base = val_s[tid];
-                const uint32_t x0 = min(4 * (bx0 + blk), a.w - 4);
-                T *p = reinterpret_cast<T *>(stage) + (size_t)(x0 - xs) * bands + c;
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t n = (uint32_t)(order >> (4 * (15 - i))) & 15;
-                    p[(n >> 2) * rowelems + (n & 3) * bands] = (T)(base + v[i]);
+                for (int i = 0; i < 16; i++) v[i] += base;
+            }
+            if (sweep) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) p[poff[i]] = (T)v[i];
+                }
+                __syncthreads();
+                for (uint32_t i = tid; i < 4 * npx; i += NT) {
+                    const uint32_t r = i / npx, px = i - r * npx;
+                    T *q = reinterpret_cast<T *>(stage) + (size_t)r * rowelems + (size_t)px * bands;
+                    for (uint32_t k = 0; k < bands; k++) {
+                        const uint32_t kc = cb[k];
+                        if (kc != k) q[k] = (T)(q[k] + q[kc]);
+                    }
+                    if (quanta > 1)
+                        for (uint32_t k = 0; k < bands; k++)
+                            q[k] = (T)dequantize_value<BITS>((uint64_t)q[k], quanta, is_signed);
+                }
+            }
+            else {
+                /* core bands first, then the derived bands add their core band's pixels: the same 16 places, one band over */
+                if (active && core == c) {
+                    if (quanta > 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = (W)dequantize_value<BITS>((uint64_t)(v[i] & TM), quanta, is_signed);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i++) p[poff[i]] = (T)v[i];
+                }
+                if (derived) {
+                    __syncthreads();
+                    if (active && core != c) {
+                        const T *q = p + core - c;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) p[poff[i]] = (T)(v[i] + q[poff[i]]);
+                    }
                 }
             }
             __syncthreads();
-            const uint32_t npx = xe - xs;
-            if (derived || quanta > 1) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
-                for (uint32_t i = tid; i < 4 * npx; i += NT) {
-                    const uint32_t r = i / npx, px = i - r * npx;
-                    T *p = reinterpret_cast<T *>(stage) + (size_t)r * rowelems + (size_t)px * bands;
-                    if (derived)
-                        for (uint32_t k = 0; k < bands; k++) {
-                            const uint32_t kc = cb[k];
-                            if (kc != k) p[k] = (T)(p[k] + p[kc]);
-                        }
-                    if (quanta > 1)
-                        for (uint32_t k = 0; k < bands; k++)
-                            p[k] = (T)dequantize_value<BITS>((uint64_t)p[k], quanta, is_signed);
-                }
-                __syncthreads();
-            }
             /* staged rows leave as the widest vectors the destination allows */
             const uint32_t rowbytes = npx * bands * (uint32_t)sizeof(T);
             for (uint32_t r = 0; r < 4; r++) {
@@ -1418,7 +1455,8 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     }
     if (err == cudaSuccess) {
         /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
-        uint32_t seg_blocks = 512 / a.bands;
+        uint32_t seg_blocks = 384 / a.bands; /* rebuild_kernel is built for at most 384 threads */
+        if (seg_blocks < 1) seg_blocks = 1;
         if (seg_blocks > nbx) seg_blocks = nbx;
         uint32_t segs = (nbx + seg_blocks - 1) / seg_blocks;
         seg_blocks = (nbx + segs - 1) / segs;

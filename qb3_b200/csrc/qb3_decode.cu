@@ -706,64 +706,75 @@ constexpr uint32_t ST_PARSED = 0x20000000u; /* scan_kernel has written the tile'
 
 /*
  * Bit buffer of scan_kernel: one stream per lane. 64 bits of look-ahead in registers, fed a 32 bit word at a time from
- * the lane's ring of 16 byte chunks in shared memory (chunk slot s of lane l at ring + (s * 32 + l) * 16), one word of
- * read-ahead. The ring itself is filled by cp.async, several chunks ahead, so neither global nor shared memory latency
- * is on the parse chain. The refill is a select, not a branch: the lanes of a warp must stay together.
+ * the lane's own ring in shared memory, one word of read-ahead. The ring is filled by cp.async in 16 byte chunks,
+ * many chunks ahead, so neither global nor shared memory latency is on the parse chain. The ring is addressed through
+ * the kernel's shared array itself (the compiler then emits LDS and predicates the refill instead of branching: the
+ * lanes of a warp refill at different times and must stay together).
  */
-template <int SLOTS> struct ScanBits {
+template <int RWORDS> struct ScanBits {
     uint64_t buf;
-    uint32_t ring;  /* shared memory address of slot 0 of this lane */
     uint32_t nb, nxt, k, w0, sh;
 
-    __device__ __forceinline__ uint32_t word(uint32_t w) const
+    __device__ __forceinline__ void open(const uint32_t *ring, uint32_t mis)
     {
-        return lds32(ring + ((w >> 2) & (SLOTS - 1)) * 512 + (w & 3) * 4);
-    }
-    __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t mis)
-    {
-        ring = ring_addr;
         w0 = mis >> 2; sh = 8 * (mis & 3);
-        buf = (uint64_t)(word(w0) >> sh);
+        buf = (uint64_t)(ring[w0] >> sh);
         nb = 32 - sh;
-        buf |= (uint64_t)word(w0 + 1) << nb;
+        buf |= (uint64_t)ring[w0 + 1] << nb;
         nb += 32;
-        nxt = word(w0 + 2);
+        nxt = ring[w0 + 2];
         k = w0 + 3;
     }
-    __device__ __forceinline__ void refill()
+    /* a select, not a branch: the lanes of a warp refill at different times, and a divergent branch costs them all
+       some fifty cycles (measured), seven times per group */
+    __device__ __forceinline__ void refill(const uint32_t *ring)
     {
         const bool take = nb <= 32;
-        const uint32_t cand = word(k); /* always loaded, kept only when the word before it moves into the buffer */
+        const uint32_t cand = ring[k & (RWORDS - 1)]; /* always loaded, kept only when the word before it moves in */
         buf |= (uint64_t)(take ? nxt : 0u) << (nb & 63);
         nb += take ? 32u : 0u;
         nxt = take ? cand : nxt;
         k += take ? 1u : 0u;
     }
-    __device__ __forceinline__ uint64_t peek() { refill(); return buf; }
-    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; } /* n <= 33, after peek() / refill() */
-    __device__ __forceinline__ uint64_t get(uint32_t n)
+    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; } /* n <= 33, after refill() */
+    /* n may carry junk above bit 4: funnel shifts in wrap mode only look at the low five bits */
+    __device__ __forceinline__ void advance_wrap(uint32_t n)
     {
-        refill();
-        const uint64_t v = buf & lowmask64(n);
-        advance(n);
-        return v;
+        const uint32_t lo = (uint32_t)buf, hi = (uint32_t)(buf >> 32);
+        buf = ((uint64_t)__funnelshift_r(hi, 0u, n) << 32) | __funnelshift_r(lo, hi, n);
     }
-    __device__ __forceinline__ uint64_t consumed() const { return 32ull * (k - 1 - w0) - sh - nb; }
+    __device__ __forceinline__ uint32_t consumed() const { return 32 * (k - 1 - w0) - sh - nb; }
 };
 
-/* 16 bytes global -> shared, the tail beyond nbytes zero filled; predicated so that the warp does not branch */
-__device__ __forceinline__ void cp_async16_zfill(bool pred, uint32_t smem_addr, const void *gmem, uint32_t nbytes)
+/* the same reader with the ring pointer inside, for the out-of-line parser of the rare groups */
+template <int RWORDS> struct ScanBitsRef {
+    ScanBits<RWORDS> b;
+    const uint32_t *ring;
+    __device__ __forceinline__ uint64_t peek() { b.refill(ring); return b.buf; }
+    __device__ __forceinline__ void advance(uint32_t n) { b.advance(n); }
+    __device__ __forceinline__ uint64_t get(uint32_t n)
+    {
+        b.refill(ring);
+        const uint64_t v = b.buf & lowmask64(n);
+        b.advance(n);
+        return v;
+    }
+};
+
+/* 16 bytes global -> shared, the tail beyond nbytes zero filled */
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void *gmem, uint32_t nbytes)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p cp.async.ca.shared.global [%1], [%2], 16, %3;\n\t}"
-                 :: "r"((uint32_t)pred), "r"(smem_addr), "l"(gmem), "r"(nbytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gmem), "r"(nbytes) : "memory");
 }
 
 /*
  * Pass one, 8 and 16 bit types: the serial part of decoding and nothing else. One stream per lane walks its groups and
  * only works out where each one starts and which rung its band is at afterwards: a 32 bit record per group,
  * (start bit << 4) | rung. Values are not decoded (common factor groups excepted: their next rung depends on the
- * values, QB3decode.h:664), nothing is reconstructed or stored, so the latency bound chain of a stream is as short
- * as it gets: per value an AND, an add and a funnel shift. rebuild_kernel then decodes all groups of a tile in parallel.
+ * values, QB3decode.h:664), nothing is reconstructed or stored, so the chain of a stream is as short as it gets:
+ * per value two ANDs, an add and a funnel shift. A lone warp per SM issues about one instruction every two cycles, so
+ * what a group costs is its instruction count: the rest of this kernel is about keeping that low.
+ * rebuild_kernel then decodes all groups of a tile in parallel.
  */
 template <typename T>
 __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups)
@@ -771,14 +782,19 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     typedef uint32_t W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
     constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
-    constexpr int VPR = BITS == 8 ? 3 : 2;      /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
-    constexpr int SLOTS = BITS == 8 ? 16 : 32, AHEAD = SLOTS - 4; /* ring chunks per lane; chunks requested ahead of the parse position */
-    constexpr int PERGROUP = BITS == 8 ? 2 : 3; /* chunks one group can consume (6 and 12 words) */
-    constexpr int NTW = (2 << U) / 8;           /* 32 bit words of a 4 bit per entry switch table */
+    constexpr int VPR = BITS == 8 ? 3 : 2;       /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
+    constexpr int RWORDS = BITS == 8 ? 64 : 128; /* ring words per lane */
+    constexpr int LSTRIDE = RWORDS + 4;          /* words between the rings of two lanes: 16 byte multiple, banks shifted */
+    constexpr int EVERY = 4;                     /* groups between ring upkeeps */
+    constexpr int GWORDS = BITS == 8 ? 6 : 12;   /* ring words one group can consume */
+    constexpr int AHEAD = RWORDS / 4 - 2;        /* chunks kept requested beyond the one being read */
+    constexpr int NTW = (2 << U) / 8;            /* 32 bit words of a 4 bit per entry switch table */
+    static_assert(4 * (AHEAD - 1) >= 2 * EVERY * GWORDS + 4, "ring too small for two upkeep intervals");
 
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x, bands = a.bands;
-    uint8_t *rb = smem + SLOTS * 512;                               /* [band][lane] running rung */
+    const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
+    uint8_t *rb = smem + 32 * LSTRIDE * 4;                          /* [band][lane] running rung */
     uint32_t *pcf = reinterpret_cast<uint32_t *>(rb + 32 * bands);  /* [band][lane] last common factor */
     uint8_t *cbs = reinterpret_cast<uint8_t *>(pcf + 32 * bands);   /* [band][lane] band map, header parsing only */
 
@@ -810,83 +826,97 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     const bool go = live && !info.bad && info.mode != M_STORED && !rle;
     if (live && !go) a.status[tile] = info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
 
+    /* the payload as 16 byte chunks from an aligned base; bytes past the end read as zero (bitstream.h:43-49) */
     const uint8_t *payload = go ? stream + info.data_off : nullptr;
     const uint64_t plen = go ? slen - info.data_off : 0;
     const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
     const uint8_t *abase = go ? payload - mis : a.streams;
-    const uint64_t span = go ? mis + plen : 0;
-    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem) + lane * 16;
+    const uint32_t span = go ? (uint32_t)(mis + plen) : 0; /* the two pass path is only taken for streams far below 4 GB */
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem) + lane * LSTRIDE * 4;
     uint32_t issued = 0; /* chunks requested so far */
-    auto request = [&](bool pred) {
-        const uint64_t start = 16ull * issued;
-        const uint32_t nbytes = start >= span ? 0u : (uint32_t)min((uint64_t)16, span - start);
-        cp_async16_zfill(pred, ring + (issued & (SLOTS - 1)) * 512, abase + (nbytes ? start : 0), nbytes);
-        issued += pred ? 1u : 0u;
+    auto request = [&]() {
+        const uint32_t start = 16 * issued;
+        const uint32_t nbytes = start >= span ? 0u : min(16u, span - start);
+        cp_async16_zfill(ring_addr + (start & (4 * RWORDS - 1)), abase + (nbytes ? start : 0), nbytes);
+        issued++;
     };
-    for (int i = 0; i < AHEAD; i++) request(true);
+    for (int i = 0; i < AHEAD; i++) request();
     cp_async_commit();
     cp_async_wait<0>();
     for (uint32_t c = 0; c < bands; c++) { rb[c * 32 + lane] = 0; pcf[c * 32 + lane] = 0; }
     __syncwarp();
 
-    ScanBits<SLOTS> s;
+    ScanBits<RWORDS> s;
     s.open(ring, mis);
     const bool ftl = info.mode == M_FTL;
     uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
 
     bool failed = false;
-    uint32_t c = 0;
+    uint32_t c = 0, upkeep = 1;
     for (uint32_t g = 0; g < ngroups; g++) {
-        /* ring upkeep: keep AHEAD chunks requested beyond the one being read; what was asked for two groups ago has landed */
-#pragma unroll
-        for (int i = 0; i < PERGROUP; i++) request(issued < (s.k >> 2) + AHEAD);
-        cp_async_commit();
-        cp_async_wait<2>();
+        /* ring upkeep every few groups: request chunks up to AHEAD beyond the one being read. What was requested one
+           upkeep ago has had EVERY groups to land and is waited for; the new requests are for reads two upkeeps away. */
+        if (--upkeep == 0) {
+            upkeep = EVERY;
+            const uint32_t want = (s.k >> 2) + AHEAD;
+            while (__any_sync(0xffffffffu, issued < want)) {
+                if (issued < want) request();
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+        }
 
         const uint32_t oldrung = rb[c * 32 + lane];
-        const uint32_t pos = (uint32_t)s.consumed();
-        s.refill();
+        const uint32_t pos = s.consumed();
+        s.refill(ring);
         const uint32_t x = (uint32_t)s.buf;
         const uint32_t idx = (x >> 1) & LMASK;
         uint32_t wl = tlen[0], wd = tdel[0];
 #pragma unroll
         for (int w = 1; w < NTW; w++) if ((idx >> 3) == (uint32_t)w) { wl = tlen[w]; wd = tdel[w]; }
         const uint32_t sft = 4 * (idx & 7);
-        const uint32_t slen_ = (x & 1) ? (wl >> sft) & 15 : 1, delta = (x & 1) ? (wd >> sft) & 15 : 0;
-        s.advance(slen_);
+        const uint32_t swl = (x & 1) ? (wl >> sft) & 15 : 1, delta = (x & 1) ? (wd >> sft) & 15 : 0;
         uint32_t r;
-        if (ftl || delta != 0 || slen_ == 1) {
+        if (ftl || delta != 0 || swl == 1) {
             r = (oldrung + delta) & UMASK;
-            /* rung 0 walks the same sixteen steps with every length forced to zero, then takes its flag and raw bits */
-            const uint32_t live_mask = r ? 1u : 0u;
+            /* rung 0: the flag and its sixteen raw bits go with the switch (QB3decode.h:148-160), and the sixteen
+               steps below run with every length forced to zero, so that all lanes walk the same code */
+            const uint32_t y = x >> swl;
+            s.advance(swl + (r ? 0u : ((y & 1) ? 17u : 1u)));
+            /* a code's length from its two low bits, x0 -> r, 01 -> r + 1, 11 -> r + 2 (QB3decode.h:119-129), as a
+               byte table in a register read with one permute; all zero at rung 0 */
+            const uint32_t lens = r ? 0x02000100u + r * 0x01010101u : 0u;
             if (BITS == 16 && r == 15) { /* two 17 bit codes exceed what one refill promises; rare */
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
-                    s.refill();
-                    const uint32_t lo = (uint32_t)s.buf;
-                    const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
-                    s.advance(r + b0 + t);
+                    s.refill(ring);
+                    s.advance(__byte_perm(lens, 0u, ((uint32_t)s.buf & 3) | 0x4440));
                 }
             }
             else {
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (i % VPR == 0) s.refill();
-                    const uint32_t lo = (uint32_t)s.buf;
-                    const uint32_t b0 = lo & live_mask, t = b0 & (lo >> 1);
-                    s.advance(r + b0 + t);
+                for (int i0 = 0; i0 < 16; i0 += VPR) {
+                    s.refill(ring);
+                    uint32_t used = 0;
+#pragma unroll
+                    for (int i = i0; i < i0 + VPR && i < 16; i++) {
+                        const uint32_t len = __byte_perm(lens, 0u, ((uint32_t)s.buf & 3) | 0x4440);
+                        s.advance_wrap(len);
+                        used += len;
+                    }
+                    s.nb -= used;
                 }
             }
-            s.refill();
-            s.advance(r ? 0u : (((uint32_t)s.buf & 1) ? 17u : 1u)); /* reference: QB3decode.h:148-160 */
         }
         else { /* common factor or index group: parsed in full, it is rare */
+            s.advance(swl);
             W sg[16];
             uint8_t rbv = (uint8_t)oldrung;
             W pc = pcf[c * 32 + lane];
-            ScanBits<SLOTS> t = s; /* a copy: the reader itself must never have its address taken, it lives in registers */
+            ScanBitsRef<RWORDS> t; /* a copy: the reader itself must never have its address taken, it lives in registers */
+            t.b = s; t.ring = ring;
             failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
-            s = t;
+            s = t.b;
             pcf[c * 32 + lane] = pc;
             r = rbv;
         }
@@ -1446,8 +1476,8 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     uint32_t *recs = nullptr;
     cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&recs), (size_t)a.ntiles * ngroups * sizeof(uint32_t), st);
     if (err != cudaSuccess) return err;
-    constexpr int SLOTS = sizeof(T) == 1 ? 16 : 32;
-    const size_t smem1 = (size_t)SLOTS * 512 + (size_t)32 * a.bands * 6;
+    constexpr int RWORDS = sizeof(T) == 1 ? 64 : 128;
+    const size_t smem1 = (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6;
     err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (err == cudaSuccess) {
         scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups);

@@ -900,11 +900,13 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
                     uint32_t used = 0;
 #pragma unroll
                     for (int i = i0; i < i0 + VPR && i < 16; i++) {
-                        const uint32_t len = __byte_perm(lens, 0u, ((uint32_t)s.buf & 3) | 0x4440);
+                        /* selector nibbles 1..3 are zero, so bytes 1..3 of len repeat the table's first byte: junk that
+                           the wrap mode shifts ignore and that cannot carry down into the sum's low byte */
+                        const uint32_t len = __byte_perm(lens, 0u, (uint32_t)s.buf & 3);
                         s.advance_wrap(len);
                         used += len;
                     }
-                    s.nb -= used;
+                    s.nb -= used & 0xff;
                 }
             }
         }

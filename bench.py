@@ -30,6 +30,8 @@ WORKLOADS = {
     "c3best": (512, 512, 8, 2, "uint16", 7, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BEST, encode+decode"),
 }
 DEFAULT_TILES = {"c2": 4096, "c3base": 1024, "c3best": 1024}
+# bytes moved to and from DRAM per launch (ncu), keyed by (workload, tiles per GPU, kernels); see profiles/
+NCU_TRAFFIC = {}
 
 
 def device_synth_tiles(ntiles, w, h, bands, dtype_code, device, t0=0, seed=12345, chunk=64):
@@ -210,6 +212,7 @@ def main():
     ap.add_argument("--ref-tiles", type=int, default=512, help="tiles per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-tiles", type=int, default=2048, help="tiles per end-to-end step")
     args = ap.parse_args()
     wl = args.workload
     if args.impl == "reference":
@@ -298,28 +301,62 @@ def main():
     raw_all = raw_rank * world
     value = raw_all / (ms_per_step * 1e-3) / 1e9
 
-    # end to end through the C ABI with host buffers: pinned host pixels -> device -> streams back to the host,
-    # then streams -> device -> pixels back to the host; all copies inside the timed region
+    # end to end through the C ABI with HOST buffers: pinned host pixels -> device -> encode -> packed streams back to
+    # the host; then host streams -> device -> decode -> pixels back to the host. Every copy is inside the timed region.
+    # The batch is cut in chunks on separate CUDA streams so that copies in both directions overlap the kernels.
     e2e = None
     if not args.no_e2e:
-        n2 = min(ntiles, 1024)
+        n2 = min(ntiles, args.e2e_tiles)
+        nch = 4 if n2 >= 64 else 1
+        per = (n2 + nch - 1) // nch
+        chunks = [(i * per, min(n2, (i + 1) * per)) for i in range(nch) if i * per < n2]
+        streams = [torch.cuda.Stream(device=dev) for _ in chunks]
         h_src = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
         h_src.copy_(src[:n2])
-        h_dst = torch.empty((n2, slot), dtype=torch.uint8).pin_memory()
-        h_sizes = torch.empty(n2, dtype=torch.int64).pin_memory()
         h_out = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
-        d_src, d_dst, d_out = src[:n2], dst[:n2], out[:n2]
+        h_packed = [torch.empty(((b - a_) * slot,), dtype=torch.uint8).pin_memory() for a_, b in chunks]
+        h_meta = [torch.empty((2 * (b - a_) + 1,), dtype=torch.int64).pin_memory() for a_, b in chunks]
+        d_packed = [torch.empty(((b - a_) * slot,), dtype=torch.uint8, device=dev) for a_, b in chunks]
+        d_meta = [torch.empty((2 * (b - a_) + 1,), dtype=torch.int64, device=dev) for a_, b in chunks]
+        totals = [0] * len(chunks)
+        torch.cuda.synchronize()
 
         def e2e_step():
-            d_src.copy_(h_src, non_blocking=True)
-            q.encode_batch(cfg, d_src, n2, dst=d_dst, sizes=sizes[:n2], status=est[:n2])
-            h_sizes.copy_(sizes[:n2], non_blocking=True)
-            h_dst.copy_(d_dst, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            d_dst.copy_(h_dst, non_blocking=True)
-            q.decode_batch(cfg, d_dst, offsets[:n2], sizes[:n2], n2, out=d_out, status=dstat[:n2])
-            h_out.copy_(d_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            moved_h2d = moved_d2h = 0
+            # encode leg
+            for i, (a_, b) in enumerate(chunks):
+                n = b - a_
+                with torch.cuda.stream(streams[i]):
+                    src[a_:b].copy_(h_src[a_:b], non_blocking=True)
+                    q.encode_batch(cfg, src[a_:b], n, dst=dst[a_:b], sizes=sizes[a_:b], status=est[a_:b])
+                    m = d_meta[i]
+                    q.pack_streams(dst[a_:b], sizes[a_:b], n, packed=d_packed[i], offsets=m[n:2 * n], total=m[2 * n:])
+                    m[:n].copy_(sizes[a_:b], non_blocking=True)
+                    h_meta[i].copy_(m, non_blocking=True)
+                moved_h2d += n * tile_bytes
+            for i, (a_, b) in enumerate(chunks):
+                n = b - a_
+                streams[i].synchronize()   # the chunk's sizes are on the host: copy exactly the bytes it produced
+                totals[i] = int(h_meta[i][2 * n])
+                with torch.cuda.stream(streams[i]):
+                    h_packed[i][:totals[i]].copy_(d_packed[i][:totals[i]], non_blocking=True)
+                moved_d2h += totals[i] + h_meta[i].numel() * 8
+            for st_ in streams:
+                st_.synchronize()
+            # decode leg: the streams come from the host buffers
+            for i, (a_, b) in enumerate(chunks):
+                n = b - a_
+                with torch.cuda.stream(streams[i]):
+                    d_packed[i][:totals[i]].copy_(h_packed[i][:totals[i]], non_blocking=True)
+                    d_meta[i].copy_(h_meta[i], non_blocking=True)
+                    m = d_meta[i]
+                    q.decode_batch(cfg, d_packed[i], m[n:2 * n], m[:n], n, out=out[a_:b], status=dstat[a_:b])
+                    h_out[a_:b].copy_(out[a_:b], non_blocking=True)
+                moved_h2d += totals[i] + h_meta[i].numel() * 8
+                moved_d2h += n * tile_bytes
+            for st_ in streams:
+                st_.synchronize()
+            return moved_h2d, moved_d2h
 
         for _ in range(2):
             e2e_step()
@@ -327,17 +364,21 @@ def main():
         t0 = time.perf_counter()
         k2 = max(3, args.steps // 2)
         for _ in range(k2):
-            e2e_step()
+            h2d_b, d2h_b = e2e_step()
         barrier()
         t_e2e = (time.perf_counter() - t0) / k2
         if world > 1:
             tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_e2e = tt.item()
-        assert torch.equal(h_out, h_src)
+        assert torch.equal(h_out, h_src), "end to end round trip differs"
+        assert not est[:n2].any().item() and not dstat[:n2].any().item()
         e2e = {"value": n2 * tile_bytes * world / t_e2e / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": n2 * tile_bytes + n2 * slot, "d2h_bytes_per_step": n2 * slot + n2 * tile_bytes + 8 * n2,
-               "tiles_per_step": n2, "note": "pinned host buffers; slots copied whole (not compacted)"}
+               "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+               "tiles_per_step": n2, "ms_per_step": 1e3 * t_e2e,
+               "note": "pinned host buffers, %d chunks on %d CUDA streams; streams packed on the device "
+                       "(qb3cu_pack_streams) before the copy back" % (len(chunks), len(chunks))}
+        del h_src, h_out, h_packed, d_packed
         # restore the device state for anything that follows
         step()
         barrier()
@@ -347,7 +388,11 @@ def main():
         enc_bytes = raw_rank + comp_bytes
         enc_gbs_hbm = enc_bytes / (enc_ms * 1e-3) / 1e9
         dec_gbs_hbm = enc_bytes / (dec_ms * 1e-3) / 1e9
-        dominant = "encode_kernel" if enc_ms >= dec_ms else "parse_kernel+finish_kernel"
+        dec_kernels = "scan_kernel+rebuild_kernel" if ts <= 2 else "parse_kernel+finish_kernel"
+        dominant = "encode_kernel" if enc_ms >= dec_ms else dec_kernels
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant pass, from the ncu --set full
+        # capture of this same command (profiles/r01_ncu_summary.md); only known for the workload it was taken on
+        traffic = NCU_TRAFFIC.get((wl, ntiles, dominant))
         dom_ach = enc_gbs_hbm if enc_ms >= dec_ms else dec_gbs_hbm
         line = {
             "metric": "QB3 encode+decode raw-pixel GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -359,7 +404,7 @@ def main():
             "encode_gbs": raw_all / (enc_ms * 1e-3) / 1e9, "decode_gbs": raw_all / (dec_ms * 1e-3) / 1e9,
             "encode_ms": enc_ms, "decode_ms": dec_ms, "compressed_ratio": comp_all / raw_all,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dom_ach, "peak": peak, "unit": "GB/s",
-                         "frac": dom_ach / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": dom_ach / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": enc_bytes,
                          "encode": {"achieved": enc_gbs_hbm, "frac": enc_gbs_hbm / peak},
                          "decode": {"achieved": dec_gbs_hbm, "frac": dec_gbs_hbm / peak}},

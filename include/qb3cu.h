@@ -103,6 +103,17 @@ LIBQB3_EXPORT int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_stre
                                      const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch,
                                      uint32_t *d_status, int ref_compat, size_t ntiles, void *stream);
 
+/*
+ * Packs the streams of qb3cu_encode_batch back to back, what a caller wants before moving them off the device or
+ * into a tile index (MRF style): stream t goes to d_packed + d_offsets[t], every start rounded up to 16 bytes;
+ * d_total[0] = bytes used. d_packed needs room for the sum of the sizes plus 16 bytes per tile (at most
+ * ntiles * slot_bytes). The result feeds qb3cu_decode_batch directly (d_streams = d_packed, d_offsets, d_sizes).
+ * (The reference hands one buffer per qb3_encode call back to its caller, cqb3.cpp:478-493; this is that step
+ * for a batch.)
+ */
+LIBQB3_EXPORT int qb3cu_pack_streams(const void *d_slots, size_t slot_bytes, const uint64_t *d_sizes, void *d_packed,
+                                     uint64_t *d_offsets, uint64_t *d_total, size_t ntiles, void *stream);
+
 /* cudaError_t of the most recent failing CUDA call made by this library on the calling thread. */
 LIBQB3_EXPORT int qb3cu_last_cuda_error(void);
 

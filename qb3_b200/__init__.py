@@ -45,6 +45,8 @@ def lib():
         L.qb3cu_encode_batch.argtypes = [cfgp, vp, sz, vp, sz, u64p, u32p, u64p, sz, vp]
         L.qb3cu_decode_batch.restype = C.c_int
         L.qb3cu_decode_batch.argtypes = [cfgp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz, vp]
+        L.qb3cu_pack_streams.restype = C.c_int
+        L.qb3cu_pack_streams.argtypes = [vp, sz, u64p, vp, u64p, u64p, sz, vp]
         L.qb3cu_last_cuda_error.restype, L.qb3cu_last_cuda_error.argtypes = C.c_int, []
         L.qb3cu_kernel_launches.restype, L.qb3cu_kernel_launches.argtypes = C.c_uint64, []
         _lib = L
@@ -129,3 +131,20 @@ def decode_batch(cfg, streams, offsets, lens, ntiles, out=None, status=None, ref
                                   tile_pitch, status.data_ptr(), int(ref_compat), ntiles, _stream_handle(stream))
     _check(rc, "qb3cu_decode_batch")
     return out, status
+
+
+def pack_streams(slots, sizes, ntiles, packed=None, offsets=None, total=None, stream=None):
+    """Pack the streams of encode_batch back to back (16 byte aligned starts). Returns (packed, offsets, total);
+    total is a 1-element int64 tensor on the device."""
+    import torch
+    dev = slots.device
+    if packed is None:
+        packed = torch.empty(slots.numel(), dtype=torch.uint8, device=dev)
+    if offsets is None:
+        offsets = torch.empty((ntiles,), dtype=torch.int64, device=dev)
+    if total is None:
+        total = torch.empty((1,), dtype=torch.int64, device=dev)
+    rc = lib().qb3cu_pack_streams(slots.data_ptr(), slots.stride(0), sizes.data_ptr(), packed.data_ptr(),
+                                  offsets.data_ptr(), total.data_ptr(), ntiles, _stream_handle(stream))
+    _check(rc, "qb3cu_pack_streams")
+    return packed, offsets, total

@@ -10,6 +10,8 @@
 namespace qb3 {
 cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st);
 cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st, uint32_t &launches);
+cudaError_t launch_pack(const uint8_t *slots, uint64_t slot, const unsigned long long *sizes, uint8_t *packed,
+                        unsigned long long *offsets, unsigned long long *total, uint32_t ntiles, cudaStream_t st);
 
 static thread_local int g_last_cuda_error = 0;
 static std::atomic<uint64_t> g_launches(0);
@@ -202,6 +204,21 @@ int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uin
     uint32_t launches = 0;
     cudaError_t err = launch_decode(a, tsize, static_cast<cudaStream_t>(stream), launches);
     count_launches(launches);
+    return note_cuda(err);
+}
+
+int qb3cu_pack_streams(const void *d_slots, size_t slot_bytes, const uint64_t *d_sizes, void *d_packed,
+                       uint64_t *d_offsets, uint64_t *d_total, size_t ntiles, void *stream)
+{
+    if (!d_slots || !d_sizes || !d_packed || !d_offsets || !d_total) return QB3CU_ERR_PARAM;
+    if (((uintptr_t)d_slots | (uintptr_t)d_packed | slot_bytes) % 16 || ntiles > 0x7fffffffull) return QB3CU_ERR_PARAM;
+    if (ntiles == 0) return QB3CU_OK;
+    cudaError_t err = launch_pack(static_cast<const uint8_t *>(d_slots), slot_bytes,
+                                  reinterpret_cast<const unsigned long long *>(d_sizes), static_cast<uint8_t *>(d_packed),
+                                  reinterpret_cast<unsigned long long *>(d_offsets),
+                                  reinterpret_cast<unsigned long long *>(d_total), (uint32_t)ntiles,
+                                  static_cast<cudaStream_t>(stream));
+    if (err == cudaSuccess) count_launches(1 + (ntiles + 65534) / 65535);
     return note_cuda(err);
 }
 

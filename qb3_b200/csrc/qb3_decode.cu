@@ -1471,11 +1471,27 @@ template <typename T> static cudaError_t launch_walk_any(const DecArgs &a, cudaS
                     : launch_walk<T, 16>(a, stage_blocks, stage_off, sstride, st);
 }
 
+/* The stream ordered allocator gives freed memory back to the driver at every synchronisation unless told to keep
+   it; the scratch of the next batch would then be mapped afresh, which costs more than the kernels. Once per device. */
+static void keep_pool_memory()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 /* scan_kernel + rebuild_kernel; the group records live in stream ordered scratch memory */
 template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, cudaStream_t st)
 {
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
     uint32_t *recs = nullptr;
+    keep_pool_memory();
     cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&recs), (size_t)a.ntiles * ngroups * sizeof(uint32_t), st);
     if (err != cudaSuccess) return err;
     constexpr int RWORDS = sizeof(T) == 1 ? 64 : 128;

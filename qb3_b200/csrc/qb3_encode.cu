@@ -824,6 +824,78 @@ __global__ void __launch_bounds__(128) rle_kernel(const __grid_constant__ EncArg
     }
 }
 
+/* ------------------------------------------------------------------ stream packing */
+
+/* offsets[t] = sum of the 16 byte rounded sizes before t, total[0] = their sum. One CTA; tiles in chunks of blockDim. */
+__global__ void __launch_bounds__(1024) pack_offsets_kernel(const unsigned long long *sizes, unsigned long long *offsets,
+                                                            unsigned long long *total, uint32_t ntiles)
+{
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long run_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) run_s = 0;
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += blockDim.x) {
+        const uint32_t t = t0 + tid;
+        const unsigned long long v = t < ntiles ? (sizes[t] + 15) & ~15ull : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = lane < (blockDim.x >> 5) ? warp_sum[lane] : 0ull, wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            warp_sum[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long run = run_s;
+        if (t < ntiles) offsets[t] = run + warp_sum[warp] + inc - v;
+        __syncthreads();
+        if (tid == blockDim.x - 1) run_s = run + warp_sum[warp] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) total[0] = run_s;
+}
+
+/* stream t moves from its slot to packed + offsets[t], 16 bytes per thread; grid (chunks, tiles) */
+__global__ void __launch_bounds__(256) pack_copy_kernel(const uint8_t *slots, uint64_t slot, const unsigned long long *sizes,
+                                                        const unsigned long long *offsets, uint8_t *packed)
+{
+    const uint32_t tile = blockIdx.y;
+    const uint64_t units = (sizes[tile] + 15) >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(slots + (uint64_t)tile * slot);
+    uint4 *dst = reinterpret_cast<uint4 *>(packed + offsets[tile]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += (uint64_t)gridDim.x * blockDim.x)
+        st_stream16(dst + i, ld_stream16(src + i));
+}
+
+cudaError_t launch_pack(const uint8_t *slots, uint64_t slot, const unsigned long long *sizes, uint8_t *packed,
+                        unsigned long long *offsets, unsigned long long *total, uint32_t ntiles, cudaStream_t st)
+{
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(sizes, offsets, total, ntiles);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    /* enough CTAs per tile to cover a slot's worth of 16 byte units with a few iterations each */
+    uint32_t chunks = (uint32_t)((slot / 16 + 256 * 8 - 1) / (256 * 8));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    for (uint32_t t0 = 0; t0 < ntiles; t0 += 65535) { /* gridDim.y limit */
+        const uint32_t n = ntiles - t0 < 65535 ? ntiles - t0 : 65535;
+        pack_copy_kernel<<<dim3(chunks, n), 256, 0, st>>>(slots + (uint64_t)t0 * slot, slot, sizes + t0, offsets + t0, packed);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
 /* ------------------------------------------------------------------ launch */
 
 template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st)

@@ -31,7 +31,10 @@ WORKLOADS = {
 }
 DEFAULT_TILES = {"c2": 4096, "c3base": 1024, "c3best": 1024}
 # bytes moved to and from DRAM per launch (ncu), keyed by (workload, tiles per GPU, kernels); see profiles/
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    ("c2", 4096, "encode_kernel"): 4.929e9,
+    ("c2", 4096, "scan_kernel+rebuild_kernel"): 2.521e9 + 5.713e9,
+}
 
 
 def device_synth_tiles(ntiles, w, h, bands, dtype_code, device, t0=0, seed=12345, chunk=64):

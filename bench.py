@@ -241,7 +241,8 @@ def main():
     slot = q.slot_bytes(cfg)
 
     # every rank owns its own contiguous shard of the tile sequence (weak scaling, no exchange)
-    src = device_synth_tiles(ntiles, w, h, bands, dcode, dev, t0=rank * ntiles)
+    t_lo, t_hi = q.shard_range(ntiles * world, rank, world)
+    src = device_synth_tiles(t_hi - t_lo, w, h, bands, dcode, dev, t0=t_lo)
     dst = torch.empty((ntiles, slot), dtype=torch.uint8, device=dev)
     sizes = torch.empty(ntiles, dtype=torch.int64, device=dev)
     est = torch.empty(ntiles, dtype=torch.int32, device=dev)

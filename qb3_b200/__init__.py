@@ -148,3 +148,11 @@ def pack_streams(slots, sizes, ntiles, packed=None, offsets=None, total=None, st
                                   offsets.data_ptr(), total.data_ptr(), ntiles, _stream_handle(stream))
     _check(rc, "qb3cu_pack_streams")
     return packed, offsets, total
+
+
+def shard_range(ntiles, rank, world):
+    """Contiguous tile range [begin, end) of one rank when a batch of ntiles independent tiles is split over world
+    GPUs (no exchange step, every rank encodes / decodes its own range; only sizes go back to the host)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank / world")
+    return ntiles * rank // world, ntiles * (rank + 1) // world

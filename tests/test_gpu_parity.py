@@ -230,3 +230,20 @@ def test_batch_decode_reports_bad_streams():
     torch.cuda.synchronize()
     assert st.cpu().numpy().tolist() == [q.TILE_OK, q.TILE_BAD_HEADER, q.TILE_CORRUPT, q.TILE_BAD_HEADER]
     assert np.array_equal(out[0].cpu().numpy().reshape(32, 32, 1), tiles[0])
+
+
+def test_pack_streams_and_decode_packed():
+    """qb3cu_pack_streams: streams back to back at 16 byte aligned offsets, decodable from there."""
+    torch = torch_mod()
+    tiles = synth_tiles(9, 100, 60, 3, np.uint8)
+    cfg, dst, sizes, status = encode_tiles(tiles, mode=MODE_BASE)
+    packed, offsets, total = q.pack_streams(dst, sizes, 9)
+    out, st = q.decode_batch(cfg, packed, offsets, sizes, 9)
+    torch.cuda.synchronize()
+    sz, off, dst_h, pk = sizes.cpu().numpy(), offsets.cpu().numpy(), dst.cpu().numpy(), packed.cpu().numpy()
+    want_off = np.concatenate([[0], np.cumsum((sz + 15) // 16 * 16)])
+    assert off.tolist() == want_off[:-1].tolist() and int(total.item()) == want_off[-1]
+    for t in range(9):
+        assert pk[off[t]:off[t] + sz[t]].tobytes() == dst_h[t, :sz[t]].tobytes()
+    assert not st.cpu().numpy().any()
+    assert np.array_equal(out.cpu().numpy().reshape(tiles.shape), tiles)

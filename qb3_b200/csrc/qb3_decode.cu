@@ -702,7 +702,14 @@ __global__ void __launch_bounds__(32, 16) walk_kernel(const DecArgs a, const uin
 
 /* ------------------------------------------------------------------ two pass decode: scan, then rebuild */
 
-constexpr uint32_t ST_PARSED = 0x20000000u; /* scan_kernel has written the tile's group records, rebuild_kernel is due */
+constexpr uint32_t ST_PARSED = 0x20000000u;   /* scan_kernel has written all of the tile's group records */
+constexpr uint32_t ST_SCANNING = 0x10000000u; /* scan_kernel is part way through the tile (the passes run in row chunks) */
+
+/* One chunk of block rows of every tile: the two passes are pipelined chunk by chunk on two streams. */
+struct RowChunk {
+    uint32_t by0, by1;  /* block rows [by0, by1) */
+    uint32_t first, last;
+};
 
 /*
  * Bit buffer of scan_kernel: one stream per lane. 64 bits of look-ahead in registers, fed a 32 bit word at a time from
@@ -777,7 +784,8 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void 
  * rebuild_kernel then decodes all groups of a tile in parallel.
  */
 template <typename T>
-__global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups)
+__global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
+                                                     const RowChunk ch, uint32_t *__restrict__ sstate)
 {
     typedef uint32_t W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -824,7 +832,7 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     }
     const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
     const bool go = live && !info.bad && info.mode != M_STORED && !rle;
-    if (live && !go) a.status[tile] = info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
+    if (live && ch.first) a.status[tile] = go ? ST_SCANNING : info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
 
     /* the payload as 16 byte chunks from an aligned base; bytes past the end read as zero (bitstream.h:43-49) */
     const uint8_t *payload = go ? stream + info.data_off : nullptr;
@@ -833,7 +841,12 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     const uint8_t *abase = go ? payload - mis : a.streams;
     const uint32_t span = go ? (uint32_t)(mis + plen) : 0; /* the two pass path is only taken for streams far below 4 GB */
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem) + lane * LSTRIDE * 4;
-    uint32_t issued = 0; /* chunks requested so far */
+    /* where this chunk picks the stream up: the reader's registers and the bands' state as the chunk before left them */
+    uint32_t *st = sstate + (size_t)(live ? tile : 0) * (6 + 2 * bands);
+    const bool resume = !ch.first && go;
+    ScanBits<RWORDS> s;
+    s.k = resume ? st[4] : 0;
+    uint32_t issued = s.k >> 2; /* chunks requested so far */
     auto request = [&]() {
         const uint32_t start = 16 * issued;
         const uint32_t nbytes = start >= span ? 0u : min(16u, span - start);
@@ -843,17 +856,26 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     for (int i = 0; i < AHEAD; i++) request();
     cp_async_commit();
     cp_async_wait<0>();
-    for (uint32_t c = 0; c < bands; c++) { rb[c * 32 + lane] = 0; pcf[c * 32 + lane] = 0; }
+    for (uint32_t c = 0; c < bands; c++) {
+        rb[c * 32 + lane] = resume ? (uint8_t)st[6 + c] : (uint8_t)0;
+        pcf[c * 32 + lane] = resume ? st[6 + bands + c] : 0u;
+    }
     __syncwarp();
 
-    ScanBits<RWORDS> s;
-    s.open(ring, mis);
+    bool failed = false;
+    if (resume) {
+        s.w0 = mis >> 2; s.sh = 8 * (mis & 3);
+        s.buf = (uint64_t)st[0] | ((uint64_t)st[1] << 32);
+        s.nb = st[2]; s.nxt = st[3];
+        failed = st[5] != 0;
+    }
+    else s.open(ring, mis);
     const bool ftl = info.mode == M_FTL;
     uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
 
-    bool failed = false;
+    const uint32_t per_row = ((a.w + 3) / 4) * bands, g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
     uint32_t c = 0, upkeep = 1;
-    for (uint32_t g = 0; g < ngroups; g++) {
+    for (uint32_t g = g_begin; g < g_end; g++) {
         /* ring upkeep every few groups: request chunks up to AHEAD beyond the one being read. What was requested one
            upkeep ago has had EVERY groups to land and is waited for; the new requests are for reads two upkeeps away. */
         if (--upkeep == 0) {
@@ -927,10 +949,14 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
         c = c + 1 == bands ? 0 : c + 1;
     }
     cp_async_wait<0>();
-    if (go) {
+    if (go && ch.last) {
         const uint64_t total = 8 * plen, used = s.consumed();
         const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
         a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : ST_PARSED;
+    }
+    else if (go) {
+        st[0] = (uint32_t)s.buf; st[1] = (uint32_t)(s.buf >> 32); st[2] = s.nb; st[3] = s.nxt; st[4] = s.k; st[5] = failed;
+        for (uint32_t c2 = 0; c2 < bands; c2++) { st[6 + c2] = rb[c2 * 32 + lane]; st[6 + bands + c2] = pcf[c2 * 32 + lane]; }
     }
 }
 
@@ -1046,7 +1072,8 @@ __device__ __forceinline__ void band_scan(uint32_t *val_s, const uint8_t *flag_s
  */
 template <typename T>
 __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups,
-                                                      const uint32_t seg_blocks, const uint32_t segs, const uint32_t rowpitch)
+                                                      const uint32_t seg_blocks, const uint32_t segs, const uint32_t rowpitch,
+                                                      const RowChunk ch, uint32_t *__restrict__ rstate)
 {
     typedef uint32_t W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -1066,7 +1093,9 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
     __shared__ uint16_t dsw[2u << U]; /* rung switch decode table */
     constexpr int VPR = BITS == 8 ? 3 : 2; /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
 
-    if (a.status[tile] != ST_PARSED) return;
+    const uint32_t tile_state = a.status[tile];
+    if (tile_state != ST_PARSED && tile_state != ST_SCANNING) return;
+    uint32_t *rst = rstate + (size_t)tile * 2 * bands; /* the bands' running value and factor between row chunks */
     const uint8_t *stream = a.streams + a.offsets[tile];
     const uint64_t slen = a.lens[tile];
     if (tid == 0) {
@@ -1078,7 +1107,10 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
         }
         bandflags = d;
     }
-    for (uint32_t c = tid; c < bands; c += NT) { carry_prev[c] = 0; carry_pcf[c] = 0; }
+    for (uint32_t c = tid; c < bands; c += NT) {
+        carry_prev[c] = ch.first ? 0u : rst[c];
+        carry_pcf[c] = ch.first ? 0u : rst[bands + c];
+    }
     for (uint32_t i = tid; i < (2u << U); i += NT) dsw[i] = (uint16_t)ds_entry(U, i);
     __syncthreads();
     const bool derived = bandflags != 0;
@@ -1102,7 +1134,7 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
         poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
     }
 
-    for (uint32_t by = 0; by < nby; by++) {
+    for (uint32_t by = ch.by0; by < ch.by1; by++) {
         const uint32_t y0 = min(4 * by, a.h - 4);
         for (uint32_t sg = 0; sg < segs; sg++) {
             const uint32_t bx0 = sg * seg_blocks, nblk = min(seg_blocks, nbx - bx0), ng = nblk * bands;
@@ -1265,7 +1297,10 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
             __syncthreads();
         }
     }
-    if (tid == 0) a.status[tile] = QB3CU_TILE_OK;
+    if (!ch.last) {
+        for (uint32_t c2 = tid; c2 < bands; c2 += NT) { rst[c2] = carry_prev[c2]; rst[bands + c2] = carry_pcf[c2]; }
+    }
+    else if (tid == 0 && tile_state == ST_PARSED) a.status[tile] = QB3CU_TILE_OK;
 }
 
 template <typename T>
@@ -1486,37 +1521,95 @@ static void keep_pool_memory()
     done[dev] = true;
 }
 
-/* scan_kernel + rebuild_kernel; the group records live in stream ordered scratch memory */
-template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, cudaStream_t st)
+/* second stream of the two pass decode, one per device, made on first use */
+static cudaStream_t aux_stream()
+{
+    static cudaStream_t aux[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!aux[dev] && cudaStreamCreateWithFlags(&aux[dev], cudaStreamNonBlocking) != cudaSuccess) aux[dev] = nullptr;
+    return aux[dev];
+}
+
+static int decode_chunks_override() /* QB3CU_CHUNKS=n: row chunks of the two pass decode, 1 = no pipelining */
+{
+    static const int v = [] { const char *e = getenv("QB3CU_CHUNKS"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+/*
+ * scan_kernel + rebuild_kernel, pipelined: the tile batch is cut into chunks of block rows, scan runs chunk after
+ * chunk on the caller's stream and hands its reader state on through memory, and the rebuild of a chunk starts on a
+ * second stream as soon as its scan is done, so that it overlaps the scan of the following chunks. scan is latency
+ * bound and leaves the SMs nearly empty; rebuild is throughput work that fills them. Plain stream / event ordering:
+ * nothing ever spins on memory. The group records and the hand-over state live in stream ordered scratch memory.
+ */
+template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, cudaStream_t st, uint32_t &launches)
 {
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
+    cudaStream_t aux = aux_stream();
+    uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : 16;
+    if (!aux) nchunks = 1;
+    if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* at least four block rows per chunk */
     uint32_t *recs = nullptr;
     keep_pool_memory();
-    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&recs), (size_t)a.ntiles * ngroups * sizeof(uint32_t), st);
+    const size_t rec_words = (size_t)a.ntiles * ngroups, ss_words = (size_t)a.ntiles * (6 + 2 * a.bands),
+                 rs_words = (size_t)a.ntiles * 2 * a.bands;
+    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&recs), (rec_words + ss_words + rs_words) * sizeof(uint32_t), st);
     if (err != cudaSuccess) return err;
+    uint32_t *sstate = recs + rec_words, *rstate = sstate + ss_words;
+
     constexpr int RWORDS = sizeof(T) == 1 ? 64 : 128;
     const size_t smem1 = (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6;
-    err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    if (err == cudaSuccess) {
-        scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups);
-        err = cudaGetLastError();
+    /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
+    uint32_t seg_blocks = 384 / a.bands; /* rebuild_kernel is built for at most 384 threads */
+    if (seg_blocks < 1) seg_blocks = 1;
+    if (seg_blocks > nbx) seg_blocks = nbx;
+    uint32_t segs = (nbx + seg_blocks - 1) / seg_blocks;
+    seg_blocks = (nbx + segs - 1) / segs;
+    segs = (nbx + seg_blocks - 1) / seg_blocks;
+    const uint32_t threads = (seg_blocks * a.bands + 31) & ~31u;
+    const uint32_t rowpitch = (seg_blocks * 4 * a.bands * (uint32_t)sizeof(T) + 15) & ~15u;
+    size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * 5 + (size_t)a.bands * 9 + 16;
+    {   /* experiment knob: QB3CU_RB_SMEM=bytes pads rebuild_kernel's shared memory to lower its occupancy */
+        static const size_t pad = [] { const char *e = getenv("QB3CU_RB_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
+        if (pad > smem2) smem2 = pad;
     }
-    if (err == cudaSuccess) {
-        /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
-        uint32_t seg_blocks = 384 / a.bands; /* rebuild_kernel is built for at most 384 threads */
-        if (seg_blocks < 1) seg_blocks = 1;
-        if (seg_blocks > nbx) seg_blocks = nbx;
-        uint32_t segs = (nbx + seg_blocks - 1) / seg_blocks;
-        seg_blocks = (nbx + segs - 1) / segs;
-        segs = (nbx + seg_blocks - 1) / seg_blocks;
-        const uint32_t threads = (seg_blocks * a.bands + 31) & ~31u;
-        const uint32_t rowpitch = (seg_blocks * 4 * a.bands * (uint32_t)sizeof(T) + 15) & ~15u;
-        const size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * 5 + (size_t)a.bands * 9 + 16;
-        err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        if (err == cudaSuccess) {
-            rebuild_kernel<T><<<a.ntiles, threads, smem2, st>>>(a, recs, ngroups, seg_blocks, segs, rowpitch);
-            err = cudaGetLastError();
+    err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+
+    cudaStream_t rst = nchunks > 1 ? aux : st;
+    for (uint32_t i = 0; i < nchunks && err == cudaSuccess; i++) {
+        RowChunk ch;
+        ch.by0 = (uint32_t)((uint64_t)nby * i / nchunks);
+        ch.by1 = (uint32_t)((uint64_t)nby * (i + 1) / nchunks);
+        ch.first = i == 0;
+        ch.last = i + 1 == nchunks;
+        scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups, ch, sstate);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) break;
+        if (nchunks > 1) {
+            cudaEvent_t ev;
+            err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (err != cudaSuccess) break;
+            err = cudaEventRecord(ev, st);
+            if (err == cudaSuccess) err = cudaStreamWaitEvent(rst, ev, 0);
+            cudaEventDestroy(ev);
+            if (err != cudaSuccess) break;
         }
+        rebuild_kernel<T><<<a.ntiles, threads, smem2, rst>>>(a, recs, ngroups, seg_blocks, segs, rowpitch, ch, rstate);
+        err = cudaGetLastError();
+        launches += 2;
+    }
+    if (nchunks > 1) { /* the caller's stream continues when the last rebuild is done */
+        cudaEvent_t ev;
+        cudaError_t e2 = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e2 == cudaSuccess) {
+            e2 = cudaEventRecord(ev, rst);
+            if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, ev, 0);
+            cudaEventDestroy(ev);
+        }
+        if (err == cudaSuccess) err = e2;
     }
     const cudaError_t ferr = cudaFreeAsync(recs, st);
     return err != cudaSuccess ? err : ferr;
@@ -1533,8 +1626,7 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaS
         /* two passes when a group's start bit fits its record (28 bits), else the single kernel */
         const uint64_t max_bits = 8 * (1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) + 1));
         if (max_bits < (1ull << 28) && !decode_path_override()) {
-            err = launch_scan_rebuild<T>(a, st);
-            launches += 2;
+            err = launch_scan_rebuild<T>(a, st, launches);
         }
         else {
             err = launch_walk_any<T>(a, st);

@@ -203,15 +203,35 @@ template <typename W> __device__ __forceinline__ void prepare_group(W (&m)[16], 
 
 /* ------------------------------------------------------------------ BEST mode helpers */
 
-/* gcd of the non-zero magnitudes of a group, 1 as soon as it is known (reference: gcf, QB3encode.h:98-126) */
+/* a % b; for magnitudes below 2^24 (8 and 16 bit data) through the float unit, which beats the integer divide
+   sequence by a factor of three: the quotient estimate is off by at most one, fixed up exactly */
+template <typename W> __device__ __forceinline__ W small_mod(W a, W b) { return a % b; }
+template <> __device__ __forceinline__ uint32_t small_mod<uint32_t>(uint32_t a, uint32_t b)
+{
+    if ((a | b) >> 24) return a % b;
+    const uint32_t q = (uint32_t)__fdividef((float)a, (float)b);
+    int32_t r = (int32_t)(a - q * b);
+    if (r < 0) r += (int32_t)b;
+    else if ((uint32_t)r >= b) r -= (int32_t)b;
+    return (uint32_t)r;
+}
+
+/* gcd of the non-zero magnitudes of a group (reference: gcf, QB3encode.h:98-126). Starting from the smallest
+   magnitude the remainders collapse at once, and nearly every group of real data is known to be 1 after a step or two. */
 template <typename W> __device__ __forceinline__ W group_gcd(const W (&m)[16])
 {
-    W g = 0;
+    W g = ~(W)0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        W a = magsabs(m[i]);
-        if (g != 1)
-            while (a) { const W t = g % a; g = a; a = t; }
+        const W a = magsabs(m[i]);
+        if (a != 0 && a < g) g = a;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (g > 1) {
+            W a = small_mod<W>(magsabs(m[i]), g);
+            while (a) { const W t = small_mod<W>(g, a); g = a; a = t; }
+        }
     }
     return g;
 }
@@ -290,6 +310,14 @@ template <typename W> struct IndexTable {
     uint64_t slots; /* 16 x 3 bits */
     __device__ bool build(const W (&m)[16])
     {
+        /* cheap exact rejection first: values hashed into 64 buckets, more than 8 buckets hit means more than 8 values */
+        uint64_t seen = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t h = (uint32_t)m[i] ^ (uint32_t)((uint64_t)m[i] >> 32);
+            seen |= 1ull << ((h * 0x9E3779B1u) >> 26);
+        }
+        if (__popcll(seen) > 8) return false;
         n = 0;
         for (int i = 0; i < 16; i++) {
             uint32_t j = 0;
@@ -559,11 +587,13 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
                    Inclusive max-scan of the committing thread index with stride 'bands', in shared memory. */
                 int last = (active && commit) ? (int)tid : -1;
                 cfm2_s[tid] = (unsigned long long)cm2;
-                for (uint32_t d = a.bands; d < ng; d <<= 1) {
-                    commit_s[tid] = last;
-                    __syncthreads();
-                    if (tid >= d && tid < ng) last = max(last, commit_s[tid - d]);
-                    __syncthreads();
+                if (__syncthreads_or(last >= 0)) { /* nobody commits a factor in most segments of real data */
+                    for (uint32_t d = a.bands; d < ng; d <<= 1) {
+                        commit_s[tid] = last;
+                        __syncthreads();
+                        if (tid >= d && tid < ng) last = max(last, commit_s[tid - d]);
+                        __syncthreads();
+                    }
                 }
                 commit_s[tid] = last;
                 __syncthreads();

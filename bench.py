@@ -28,8 +28,11 @@ WORKLOADS = {
     "c2": (512, 512, 3, 0, "uint8", 8, None, "4096 tiles 512x512x3 u8, QB3M_FTL lossless, encode+decode"),
     "c3base": (512, 512, 8, 2, "uint16", 4, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BASE, encode+decode"),
     "c3best": (512, 512, 8, 2, "uint16", 7, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BEST, encode+decode"),
+    "c4i32": (512, 512, 1, 5, "int32", 8, None, "tiles 512x512x1 i32, QB3M_FTL lossless, encode+decode"),
+    "c4u64q3": (512, 512, 1, 6, "uint64", 4, None, "tiles 512x512x1 u64, QB3M_BASE quanta 3, encode+decode"),
 }
-DEFAULT_TILES = {"c2": 4096, "c3base": 1024, "c3best": 1024}
+QUANTA = {"c4u64q3": 3}
+DEFAULT_TILES = {"c2": 4096, "c3base": 1024, "c3best": 1024, "c4i32": 2048, "c4u64q3": 1024}
 # bytes moved to and from DRAM per launch (ncu), keyed by (workload, tiles per GPU, kernels); see profiles/
 NCU_TRAFFIC = {
     ("c2", 4096, "encode_kernel"): 4.929e9,
@@ -150,7 +153,7 @@ def run_reference_arm(args, wl):
     times = []
     for i in range(args.warmup + args.steps):
         e, d = C.c_double(), C.c_double()
-        rc = bench.refbench_run(REF_SO.encode(), ntiles, w, h, bands, dcode, mode, cb, 1, tiles.ctypes.data,
+        rc = bench.refbench_run(REF_SO.encode(), ntiles, w, h, bands, dcode, mode, cb, QUANTA.get(wl, 1), tiles.ctypes.data,
                                 streams.ctypes.data, slot, sizes.ctypes.data, None, ncores, 1, C.byref(e), C.byref(d))
         if rc:
             print(json.dumps({"impl": "reference", "unavailable": "refbench_run failed rc=%d" % rc}))
@@ -194,7 +197,7 @@ def cpu_baseline(wl, ntiles=256):
     cb = (C.c_size_t * 256)(*cband) if cband else None
     e, d = C.c_double(), C.c_double()
     reps = 3
-    rc = bench.refbench_run(REF_SO.encode(), ntiles, w, h, bands, dcode, mode, cb, 1, tiles.ctypes.data, streams.ctypes.data,
+    rc = bench.refbench_run(REF_SO.encode(), ntiles, w, h, bands, dcode, mode, cb, QUANTA.get(wl, 1), tiles.ctypes.data, streams.ctypes.data,
                             slot, sizes.ctypes.data, None, ncores, reps, C.byref(e), C.byref(d))
     if rc:
         return None
@@ -237,7 +240,7 @@ def main():
     ntiles = args.tiles or DEFAULT_TILES[wl]
     ts = q.TYPESIZE[dcode]
     tile_bytes = w * h * bands * ts
-    cfg = q.config(w, h, bands, dcode, mode=mode, cband=cband)
+    cfg = q.config(w, h, bands, dcode, mode=mode, cband=cband, quanta=QUANTA.get(wl, 1))
     slot = q.slot_bytes(cfg)
 
     # every rank owns its own contiguous shard of the tile sequence (weak scaling, no exchange)
@@ -270,7 +273,7 @@ def main():
         step()
     barrier()
     assert not est.any().item() and not dstat.any().item(), "tile status reports an error"
-    assert torch.equal(out, src), "decode(encode(x)) != x"
+    assert wl in QUANTA or torch.equal(out, src), "decode(encode(x)) != x"
     comp_bytes = int(sizes.sum().item())
 
     sampler = ClockSampler(local)
@@ -375,7 +378,7 @@ def main():
             tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             t_e2e = tt.item()
-        assert torch.equal(h_out, h_src), "end to end round trip differs"
+        assert wl in QUANTA or torch.equal(h_out, h_src), "end to end round trip differs"
         assert not est[:n2].any().item() and not dstat[:n2].any().item()
         e2e = {"value": n2 * tile_bytes * world / t_e2e / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),

@@ -14,6 +14,7 @@
  * per block row (QB3decode.h:730-737) and at the end (QB3decode.cpp:434-450).
  */
 #include <cstdlib>
+#include <type_traits>
 
 #include "qb3_device.cuh"
 
@@ -960,6 +961,161 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     }
 }
 
+/* Position based reader over a lane's ring, for the 32 and 64 bit scan: codes there can be 65 bits, so nothing is
+   buffered in registers; a read takes the words it needs from shared memory. Position is in bits from the ring's origin. */
+template <int RWORDS> struct RingBits {
+    const uint32_t *ring;
+    uint32_t pos;
+    __device__ __forceinline__ uint32_t peek32() const
+    {
+        const uint32_t w = pos >> 5;
+        return __funnelshift_r(ring[w & (RWORDS - 1)], ring[(w + 1) & (RWORDS - 1)], pos & 31);
+    }
+    __device__ __forceinline__ uint64_t peek() const
+    {
+        const uint32_t w = pos >> 5, sh = pos & 31;
+        const uint32_t w0 = ring[w & (RWORDS - 1)], w1 = ring[(w + 1) & (RWORDS - 1)], w2 = ring[(w + 2) & (RWORDS - 1)];
+        return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+    }
+    __device__ __forceinline__ void advance(uint64_t n) { pos += (uint32_t)n; }
+    __device__ __forceinline__ uint64_t get(uint32_t n)
+    {
+        const uint64_t v = peek() & lowmask64(n);
+        pos += n;
+        return v;
+    }
+};
+
+/*
+ * Pass one for 32 and 64 bit types. Same job and same hand-over as scan_kernel -- one stream per lane, a record
+ * (start bit << 6) | rung per group, reader state passed from row chunk to row chunk -- but the chain is kept simple:
+ * a bit position, and per value the two low bits of its code read from the ring. These types have a quarter or an
+ * eighth of the groups per byte of the 8 bit case, so the per group cost matters that much less.
+ */
+template <typename T>
+__global__ void __launch_bounds__(32, 1) scan_wide_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
+                                                          const RowChunk ch, unsigned long long *__restrict__ sstate)
+{
+    typedef typename traits<T>::W W;
+    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
+    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
+    constexpr int RWORDS = 256;                  /* ring words per lane */
+    constexpr int LSTRIDE = RWORDS + 4;
+    constexpr int EVERY = 2;                     /* groups between ring upkeeps */
+    constexpr int GWORDS = (16 * (BITS + 2) + 3 * BITS + 64) / 32 + 3; /* ring words one group of any kind can consume */
+    constexpr int AHEAD = RWORDS / 4 - 2;
+    static_assert(4 * (AHEAD - 1) >= 2 * EVERY * GWORDS + 4, "ring too small for two upkeep intervals");
+
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x, bands = a.bands;
+    const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
+    W *pcf = reinterpret_cast<W *>(smem + 32 * LSTRIDE * 4);              /* [band][lane] last common factor */
+    uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + 32 * bands);           /* [band][lane] running rung */
+    uint8_t *cbs = rb + 32 * bands;                                        /* [band][lane] band map, header parsing only */
+    uint16_t *dsw = reinterpret_cast<uint16_t *>(cbs + 32 * bands + ((32 * bands) & 1)); /* rung switch decode table */
+    for (uint32_t i = lane; i < (2u << U); i += 32) dsw[i] = (uint16_t)ds_entry(U, i);
+
+    const uint32_t tile = blockIdx.x * 32 + lane;
+    const bool live = tile < a.ntiles;
+    const uint8_t *stream = nullptr;
+    uint64_t slen = 0;
+    StreamInfo info;
+    info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
+    if (live) {
+        stream = a.streams + a.offsets[tile];
+        slen = a.lens[tile];
+        parse_header(stream, slen, a, info, cbs + lane, 32);
+    }
+    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
+    const bool go = live && !info.bad && info.mode != M_STORED && !rle;
+    if (live && ch.first) a.status[tile] = go ? ST_SCANNING : info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
+
+    const uint8_t *payload = go ? stream + info.data_off : nullptr;
+    const uint64_t plen = go ? slen - info.data_off : 0;
+    const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
+    const uint8_t *abase = go ? payload - mis : a.streams;
+    const uint32_t span = go ? (uint32_t)(mis + plen) : 0;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem) + lane * LSTRIDE * 4;
+    unsigned long long *st = sstate + (size_t)(live ? tile : 0) * (2 + 2 * bands);
+    const bool resume = !ch.first && go;
+    RingBits<RWORDS> s;
+    s.ring = ring;
+    s.pos = resume ? (uint32_t)st[0] : 8 * mis;
+    bool failed = resume ? st[1] != 0 : false;
+    uint32_t issued = s.pos >> 7;
+    auto request = [&]() {
+        const uint32_t start = 16 * issued;
+        const uint32_t nbytes = start >= span ? 0u : min(16u, span - start);
+        cp_async16_zfill(ring_addr + (start & (4 * RWORDS - 1)), abase + (nbytes ? start : 0), nbytes);
+        issued++;
+    };
+    for (int i = 0; i < AHEAD; i++) request();
+    cp_async_commit();
+    cp_async_wait<0>();
+    for (uint32_t c = 0; c < bands; c++) {
+        rb[c * 32 + lane] = resume ? (uint8_t)st[2 + c] : (uint8_t)0;
+        pcf[c * 32 + lane] = resume ? (W)st[2 + bands + c] : (W)0;
+    }
+    __syncwarp();
+
+    const bool ftl = info.mode == M_FTL;
+    uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
+    const uint32_t per_row = ((a.w + 3) / 4) * bands, g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
+    uint32_t c = 0, upkeep = 1;
+    for (uint32_t g = g_begin; g < g_end; g++) {
+        if (--upkeep == 0) {
+            upkeep = EVERY;
+            const uint32_t want = (s.pos >> 7) + AHEAD;
+            while (__any_sync(0xffffffffu, issued < want)) {
+                if (issued < want) request();
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+        }
+        const uint32_t oldrung = rb[c * 32 + lane];
+        const uint32_t pos = s.pos - 8 * mis;
+        const uint32_t x = s.peek32();
+        const uint32_t cs = (x & 1) ? dsw[(x >> 1) & LMASK] : 0u;
+        s.pos += (x & 1) ? cs >> 12 : 1;
+        uint32_t r;
+        if (ftl || (cs & 0xfff) != 0 || cs == 0) {
+            r = (oldrung + cs) & UMASK;
+            if (r == 0) s.pos += (s.peek32() & 1) ? 17 : 1; /* reference: QB3decode.h:148-160 */
+            else {
+#pragma unroll 4
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t y = s.peek32();
+                    const uint32_t b0 = y & 1, t = b0 & (y >> 1);
+                    s.pos += r + b0 + t;
+                }
+            }
+        }
+        else { /* common factor or index group: parsed in full, it is rare */
+            W sg[16];
+            uint8_t rbv = (uint8_t)oldrung;
+            W pc = pcf[c * 32 + lane];
+            RingBits<RWORDS> t = s;
+            failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
+            s.pos = t.pos;
+            pcf[c * 32 + lane] = pc;
+            r = rbv;
+        }
+        rb[c * 32 + lane] = (uint8_t)r;
+        if (go) rec[g] = (pos << 6) | r;
+        c = c + 1 == bands ? 0 : c + 1;
+    }
+    cp_async_wait<0>();
+    if (go && ch.last) {
+        const uint64_t total = 8 * plen, used = s.pos - 8 * mis;
+        const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
+        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : ST_PARSED;
+    }
+    else if (go) {
+        st[0] = s.pos; st[1] = failed;
+        for (uint32_t c2 = 0; c2 < bands; c2++) { st[2 + c2] = rb[c2 * 32 + lane]; st[2 + bands + c2] = pcf[c2 * 32 + lane]; }
+    }
+}
+
 /* Bit reader of rebuild_kernel: a thread reads one group at a known bit position straight from global memory
    (neighbouring threads read neighbouring words). Same contract as the others: 33 valid bits after refill(), zeros
    past the end of the payload. */
@@ -1011,27 +1167,66 @@ struct GroupBits {
     }
 };
 
+/* The same for 32 and 64 bit types, where one code can be 65 bits long: no register buffer, just a bit position;
+   peek() assembles 64 bits from three words. Slower per value, which a throughput kernel can afford. */
+struct WideBits {
+    const uint32_t *base;
+    uint64_t pos; /* bit position from base */
+    uint32_t nwords, tailmask;
+
+    __device__ __forceinline__ uint32_t load(uint64_t i) const
+    {
+        uint32_t w = i < nwords ? __ldg(base + i) : 0u;
+        if (i + 1 == nwords) w &= tailmask;
+        return w;
+    }
+    __device__ __forceinline__ void open(const uint8_t *payload, uint64_t plen, uint64_t bit)
+    {
+        const uint32_t mis = (uint32_t)((uintptr_t)payload & 3);
+        const uint64_t span = mis + plen;
+        const uint32_t tail = (uint32_t)span & 3;
+        base = reinterpret_cast<const uint32_t *>(payload - mis);
+        nwords = (uint32_t)((span + 3) >> 2);
+        tailmask = tail ? (1u << (8 * tail)) - 1 : 0xffffffffu;
+        pos = bit + 8 * mis;
+    }
+    __device__ __forceinline__ uint64_t peek() const
+    {
+        const uint64_t k = pos >> 5;
+        const uint32_t sh = (uint32_t)pos & 31;
+        const uint32_t w0 = load(k), w1 = load(k + 1), w2 = load(k + 2);
+        return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+    }
+    __device__ __forceinline__ void advance(uint64_t n) { pos += n; }
+    __device__ __forceinline__ uint64_t get(uint32_t n)
+    {
+        const uint64_t v = peek() & lowmask64(n);
+        pos += n;
+        return v;
+    }
+};
+
 /*
  * Per band scan over the threads of a segment, thread t = block * bands + band: warp w takes bands w, w + nwarps, ...
  * and runs along the band's blocks 32 at a time. ADD: exclusive prefix sum of val, seeded and continued by carry[band].
  * LAST: the val of the latest earlier thread of the band with flag set, else carry[band]; carry moves on likewise.
  * val_s / flag_s are shared arrays indexed by thread; results replace val_s. Call with all threads, between barriers.
  */
-template <bool LAST>
-__device__ __forceinline__ void band_scan(uint32_t *val_s, const uint8_t *flag_s, uint32_t *carry, uint32_t nblk, uint32_t bands)
+template <bool LAST, typename V>
+__device__ __forceinline__ void band_scan(V *val_s, const uint8_t *flag_s, V *carry, uint32_t nblk, uint32_t bands)
 {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (uint32_t c = warp; c < bands; c += nwarps) {
-        uint32_t run = carry[c];
+        V run = carry[c];
         for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
             const uint32_t b = b0 + lane, t = b * bands + c;
             const bool in = b < nblk;
-            uint32_t v = in ? val_s[t] : 0u;
+            V v = in ? val_s[t] : (V)0;
             if (!LAST) {
-                uint32_t inc = v;
+                V inc = v;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                    const V o = __shfl_up_sync(0xffffffffu, inc, d);
                     if (lane >= d) inc += o;
                 }
                 if (in) val_s[t] = run + inc - v;
@@ -1039,20 +1234,21 @@ __device__ __forceinline__ void band_scan(uint32_t *val_s, const uint8_t *flag_s
             }
             else {
                 uint32_t f = in && flag_s[t] ? 1u : 0u;
-                const uint32_t own_v = v, own_f = f;
                 /* inclusive "last flagged" scan */
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t ov = __shfl_up_sync(0xffffffffu, v, d), of = __shfl_up_sync(0xffffffffu, f, d);
+                    const V ov = __shfl_up_sync(0xffffffffu, v, d);
+                    const uint32_t of = __shfl_up_sync(0xffffffffu, f, d);
                     if (lane >= d && !f) { v = ov; f = of; }
                 }
                 /* exclusive: what the previous lane ended with */
-                uint32_t pv = __shfl_up_sync(0xffffffffu, v, 1), pf = __shfl_up_sync(0xffffffffu, f, 1);
+                const V pv = __shfl_up_sync(0xffffffffu, v, 1);
+                uint32_t pf = __shfl_up_sync(0xffffffffu, f, 1);
                 if (lane == 0) pf = 0;
                 if (in) val_s[t] = pf ? pv : run;
-                const uint32_t lv = __shfl_sync(0xffffffffu, v, 31), lf = __shfl_sync(0xffffffffu, f, 31);
+                const V lv = __shfl_sync(0xffffffffu, v, 31);
+                const uint32_t lf = __shfl_sync(0xffffffffu, f, 31);
                 if (lf) run = lv;
-                (void)own_v; (void)own_f;
             }
         }
         if (lane == 0) carry[c] = run;
@@ -1071,21 +1267,24 @@ __device__ __forceinline__ void band_scan(uint32_t *val_s, const uint8_t *flag_s
  *      bands (QB3decode.h:730-737) and quanta multiplied (QB3decode.cpp:77-107), and the rows leave as 16 byte vectors
  */
 template <typename T>
-__global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups,
-                                                      const uint32_t seg_blocks, const uint32_t segs, const uint32_t rowpitch,
-                                                      const RowChunk ch, uint32_t *__restrict__ rstate)
+__global__ void __launch_bounds__(sizeof(T) <= 2 ? 384 : 256, 2)
+rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups, const uint32_t seg_blocks,
+               const uint32_t segs, const uint32_t rowpitch, const RowChunk ch, unsigned long long *__restrict__ rstate)
 {
-    typedef uint32_t W;
+    typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
+    constexpr bool NARROW = BITS <= 16;
     constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
-    constexpr W TM = (W)((1ull << BITS) - 1);
+    constexpr uint32_t RBITS = NARROW ? 4 : 6, RMASK = (1u << RBITS) - 1; /* record = (start bit << RBITS) | rung */
+    const W TM = (W)lowmask64(BITS);
+    typedef typename std::conditional<NARROW, GroupBits, WideBits>::type Bits;
 
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, NT = blockDim.x, tile = blockIdx.x, bands = a.bands;
     uint8_t *stage = smem;                                                  /* [4][rowpitch] */
-    uint32_t *val_s = reinterpret_cast<uint32_t *>(stage + 4 * rowpitch);   /* [NT] */
-    uint32_t *carry_prev = val_s + NT;                                      /* [bands] */
-    uint32_t *carry_pcf = carry_prev + bands;                               /* [bands] */
+    W *val_s = reinterpret_cast<W *>(stage + 4 * rowpitch);                 /* [NT] */
+    W *carry_prev = val_s + NT;                                             /* [bands] */
+    W *carry_pcf = carry_prev + bands;                                      /* [bands] */
     uint8_t *flag_s = reinterpret_cast<uint8_t *>(carry_pcf + bands);       /* [NT] */
     uint8_t *cb = flag_s + NT;                                              /* [bands] */
     __shared__ StreamInfo info;
@@ -1095,7 +1294,7 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
 
     const uint32_t tile_state = a.status[tile];
     if (tile_state != ST_PARSED && tile_state != ST_SCANNING) return;
-    uint32_t *rst = rstate + (size_t)tile * 2 * bands; /* the bands' running value and factor between row chunks */
+    unsigned long long *rst = rstate + (size_t)tile * 2 * bands; /* the bands' running value and factor between row chunks */
     const uint8_t *stream = a.streams + a.offsets[tile];
     const uint64_t slen = a.lens[tile];
     if (tid == 0) {
@@ -1108,8 +1307,8 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
         bandflags = d;
     }
     for (uint32_t c = tid; c < bands; c += NT) {
-        carry_prev[c] = ch.first ? 0u : rst[c];
-        carry_pcf[c] = ch.first ? 0u : rst[bands + c];
+        carry_prev[c] = ch.first ? (W)0 : (W)rst[c];
+        carry_pcf[c] = ch.first ? (W)0 : (W)rst[bands + c];
     }
     for (uint32_t i = tid; i < (2u << U); i += NT) dsw[i] = (uint16_t)ds_entry(U, i);
     __syncthreads();
@@ -1143,22 +1342,24 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
             const uint32_t g = (by * nbx + bx0) * bands + tid;
 
             W v[16];
-            uint32_t tot = 0;
+            W tot = 0;
             uint32_t kind = 0; /* 1: common factor group that reuses the band's factor, 2: one that wrote a new factor */
             uint32_t oldrung = 0, pos = 0;
             if (active) {
-                pos = rec[g] >> 4;
-                oldrung = g >= bands ? rec[g - bands] & 15 : 0;
-                GroupBits s;
+                pos = rec[g] >> RBITS;
+                oldrung = g >= bands ? rec[g - bands] & RMASK : 0;
+                Bits s;
                 s.open(payload, plen, pos);
                 uint32_t cs = 0;
                 {
-                    const uint32_t x = (uint32_t)s.buf; /* open() left at least 33 bits */
+                    const uint32_t x = (uint32_t)s.peek(); /* narrow: open() left at least 33 bits */
                     if (x & 1) cs = dsw[(x >> 1) & LMASK];
                     s.advance((x & 1) ? cs >> 12 : 1);
                 }
                 if (ftl || (cs & 0xfff) != 0 || cs == 0) {
                     const uint32_t r = (oldrung + cs) & UMASK;
+                    if constexpr (!NARROW) read_group<W>(s, r, v, !ftl); /* reference: QB3decode.h:142-290 */
+                    else {
                     if (r == 0) {
                         s.refill();
                         const uint32_t y = (uint32_t)s.buf;
@@ -1187,17 +1388,18 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
                             for (int i = 0; i < 16; i++) if (i == k) v[i] ^= 1u << r;
                         }
                     }
+                    }
                 }
                 else { /* common factor or index group; a reused factor is not known yet: parse with 0, redo below */
-                    GroupBits t = s;
+                    Bits t = s;
                     uint8_t rbv = (uint8_t)oldrung;
-                    W pc = 0xffffffffu;
+                    W pc = 0;
                     W sgv[16]; /* the out-of-line parser takes an array by reference: keep that one out of v's registers */
                     read_special_group<W, BITS, U>(t, sgv, rbv, pc);
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] = sgv[i];
                     /* what kind it was: the flag after the signal and the switch (QB3decode.h:624-640) */
-                    GroupBits p = s;
+                    Bits p = s;
                     const uint32_t e = ds_entry(U, (uint32_t)p.peek() & LMASK);
                     p.advance((e >> 12) - 1);
                     if (((oldrung + e) & UMASK) != UMASK) kind = p.get(1) ? 2 : 1;
@@ -1209,10 +1411,10 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
                 val_s[tid] = tot;
                 flag_s[tid] = kind == 2;
                 __syncthreads();
-                band_scan<true>(val_s, flag_s, carry_pcf, nblk, bands);
+                band_scan<true, W>(val_s, flag_s, carry_pcf, nblk, bands);
                 __syncthreads();
                 if (kind == 1) {
-                    GroupBits s;
+                    Bits s;
                     s.open(payload, plen, pos);
                     s.advance(1 + (cs_signal(U) >> 12) - 1);
                     uint8_t rbv = (uint8_t)oldrung;
@@ -1232,12 +1434,12 @@ __global__ void __launch_bounds__(384, 2) rebuild_kernel(const DecArgs a, const 
             }
             val_s[tid] = tot;
             __syncthreads();
-            band_scan<false>(val_s, nullptr, carry_prev, nblk, bands);
+            band_scan<false, W>(val_s, nullptr, carry_prev, nblk, bands);
             __syncthreads();
             const uint32_t npx = xe - xs;
             T *p = reinterpret_cast<T *>(stage) + (size_t)(min(4 * (bx0 + blk), a.w - 4) - xs) * bands + c;
             if (active) {
-                const uint32_t base = val_s[tid];
+                const W base = val_s[tid];
 #pragma unroll
                 for (int i = 0; i < 16; i++) v[i] += base;
             }
@@ -1546,23 +1748,29 @@ static int decode_chunks_override() /* QB3CU_CHUNKS=n: row chunks of the two pas
  */
 template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, cudaStream_t st, uint32_t &launches)
 {
+    constexpr bool NARROW = sizeof(T) <= 2;
+    typedef typename traits<T>::W W;
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
     cudaStream_t aux = aux_stream();
     uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : 16;
     if (!aux) nchunks = 1;
     if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* at least four block rows per chunk */
-    uint32_t *recs = nullptr;
+    uint8_t *scratch = nullptr;
     keep_pool_memory();
-    const size_t rec_words = (size_t)a.ntiles * ngroups, ss_words = (size_t)a.ntiles * (6 + 2 * a.bands),
-                 rs_words = (size_t)a.ntiles * 2 * a.bands;
-    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&recs), (rec_words + ss_words + rs_words) * sizeof(uint32_t), st);
+    const size_t rec_bytes = ((size_t)a.ntiles * ngroups * sizeof(uint32_t) + 15) & ~(size_t)15,
+                 ss_bytes = (size_t)a.ntiles * (2 + 2 * a.bands) * 8, rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8;
+    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, st);
     if (err != cudaSuccess) return err;
-    uint32_t *sstate = recs + rec_words, *rstate = sstate + ss_words;
+    uint32_t *recs = reinterpret_cast<uint32_t *>(scratch);
+    void *sstate = scratch + rec_bytes;
+    unsigned long long *rstate = reinterpret_cast<unsigned long long *>(scratch + rec_bytes + ss_bytes);
 
-    constexpr int RWORDS = sizeof(T) == 1 ? 64 : 128;
-    const size_t smem1 = (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6;
+    constexpr int RWORDS = sizeof(T) == 1 ? 64 : sizeof(T) == 2 ? 128 : 256;
+    const size_t smem1 = NARROW ? (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6
+                                : (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * (sizeof(W) + 2) + 2 + 2 * (2u << traits<T>::U);
     /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
-    uint32_t seg_blocks = 384 / a.bands; /* rebuild_kernel is built for at most 384 threads */
+    const uint32_t max_threads = NARROW ? 384 : 256; /* what rebuild_kernel is built for */
+    uint32_t seg_blocks = max_threads / a.bands;
     if (seg_blocks < 1) seg_blocks = 1;
     if (seg_blocks > nbx) seg_blocks = nbx;
     uint32_t segs = (nbx + seg_blocks - 1) / seg_blocks;
@@ -1570,12 +1778,13 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     segs = (nbx + seg_blocks - 1) / seg_blocks;
     const uint32_t threads = (seg_blocks * a.bands + 31) & ~31u;
     const uint32_t rowpitch = (seg_blocks * 4 * a.bands * (uint32_t)sizeof(T) + 15) & ~15u;
-    size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * 5 + (size_t)a.bands * 9 + 16;
+    size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * (sizeof(W) + 1) + (size_t)a.bands * (2 * sizeof(W) + 1) + 16;
     {   /* experiment knob: QB3CU_RB_SMEM=bytes pads rebuild_kernel's shared memory to lower its occupancy */
         static const size_t pad = [] { const char *e = getenv("QB3CU_RB_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
         if (pad > smem2) smem2 = pad;
     }
-    err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if constexpr (NARROW) err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    else err = cudaFuncSetAttribute(scan_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
 
     cudaStream_t rst = nchunks > 1 ? aux : st;
@@ -1585,7 +1794,10 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         ch.by1 = (uint32_t)((uint64_t)nby * (i + 1) / nchunks);
         ch.first = i == 0;
         ch.last = i + 1 == nchunks;
-        scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups, ch, sstate);
+        if constexpr (NARROW)
+            scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups, ch, static_cast<uint32_t *>(sstate));
+        else
+            scan_wide_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups, ch, static_cast<unsigned long long *>(sstate));
         err = cudaGetLastError();
         if (err != cudaSuccess) break;
         if (nchunks > 1) {
@@ -1611,7 +1823,7 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         }
         if (err == cudaSuccess) err = e2;
     }
-    const cudaError_t ferr = cudaFreeAsync(recs, st);
+    const cudaError_t ferr = cudaFreeAsync(scratch, st);
     return err != cudaSuccess ? err : ferr;
 }
 
@@ -1622,18 +1834,22 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaS
     cudaError_t err;
     bool walked = false;
     launches = 0;
-    if constexpr (sizeof(T) <= 2) if (a.w >= 4 && a.h >= 4) {
-        /* two passes when a group's start bit fits its record (28 bits), else the single kernel */
+    if (a.w >= 4 && a.h >= 4) {
+        /* two passes when a group's start bit fits its record (28 bits, 26 for the wide types); else the single
+           kernel for 8 / 16 bit types and the general path for the others */
         const uint64_t max_bits = 8 * (1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) + 1));
-        if (max_bits < (1ull << 28) && !decode_path_override()) {
+        const uint32_t pos_bits = sizeof(T) <= 2 ? 28 : 26;
+        if (max_bits < (1ull << pos_bits) && !decode_path_override()) {
             err = launch_scan_rebuild<T>(a, st, launches);
+            if (err != cudaSuccess) return err;
+            walked = true;
         }
-        else {
+        else if constexpr (sizeof(T) <= 2) {
             err = launch_walk_any<T>(a, st);
             launches += 1;
+            if (err != cudaSuccess) return err;
+            walked = true;
         }
-        if (err != cudaSuccess) return err;
-        walked = true;
     }
     const size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
     err = cudaFuncSetAttribute(parse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

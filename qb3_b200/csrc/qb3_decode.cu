@@ -720,37 +720,46 @@ struct RowChunk {
  * lanes of a warp refill at different times and must stay together).
  */
 template <int RWORDS> struct ScanBits {
-    uint64_t buf;
+    uint32_t lo, mid, hi; /* 96 bits of look-ahead; the parse chain only ever reads lo */
     uint32_t nb, nxt, k, w0, sh;
 
     __device__ __forceinline__ void open(const uint32_t *ring, uint32_t mis)
     {
         w0 = mis >> 2; sh = 8 * (mis & 3);
-        buf = (uint64_t)(ring[w0] >> sh);
-        nb = 32 - sh;
-        buf |= (uint64_t)ring[w0 + 1] << nb;
-        nb += 32;
-        nxt = ring[w0 + 2];
-        k = w0 + 3;
+        const uint32_t a = ring[w0], b = ring[w0 + 1], c = ring[w0 + 2];
+        lo = __funnelshift_r(a, b, sh);
+        mid = __funnelshift_r(b, c, sh);
+        hi = c >> sh;
+        nb = 96 - sh;
+        nxt = ring[w0 + 3];
+        k = w0 + 4;
     }
-    /* a select, not a branch: the lanes of a warp refill at different times, and a divergent branch costs them all
-       some fifty cycles (measured), seven times per group */
+    /*
+     * Tops the buffer up to at least 64 bits. Called with at least 32 bits in it (every caller consumes at most 32
+     * between two calls), so the new word lands in mid / hi and never in lo: the chain, which reads lo, does not
+     * wait for the refill, and the refill's own dependency (how many bits the last values took) stays off the chain.
+     * A select, not a branch: the lanes of a warp refill at different times, and a divergent branch costs them all
+     * some fifty cycles (measured), seven times per group.
+     */
     __device__ __forceinline__ void refill(const uint32_t *ring)
     {
-        const bool take = nb <= 32;
+        const bool take = nb <= 64;
         const uint32_t cand = ring[k & (RWORDS - 1)]; /* always loaded, kept only when the word before it moves in */
-        buf |= (uint64_t)(take ? nxt : 0u) << (nb & 63);
+        const uint64_t x = (uint64_t)(take ? nxt : 0u) << ((nb - 32) & 63);
+        mid |= (uint32_t)x;
+        hi |= (uint32_t)(x >> 32);
         nb += take ? 32u : 0u;
         nxt = take ? cand : nxt;
         k += take ? 1u : 0u;
     }
-    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; } /* n <= 33, after refill() */
-    /* n may carry junk above bit 4: funnel shifts in wrap mode only look at the low five bits */
-    __device__ __forceinline__ void advance_wrap(uint32_t n)
+    /* n < 32; it may carry junk above bit 4: funnel shifts in wrap mode only look at the low five bits */
+    __device__ __forceinline__ void shift(uint32_t n)
     {
-        const uint32_t lo = (uint32_t)buf, hi = (uint32_t)(buf >> 32);
-        buf = ((uint64_t)__funnelshift_r(hi, 0u, n) << 32) | __funnelshift_r(lo, hi, n);
+        lo = __funnelshift_r(lo, mid, n);
+        mid = __funnelshift_r(mid, hi, n);
+        hi = __funnelshift_r(hi, 0u, n);
     }
+    __device__ __forceinline__ void advance(uint32_t n) { shift(n); nb -= n; } /* n < 32, after refill() */
     __device__ __forceinline__ uint32_t consumed() const { return 32 * (k - 1 - w0) - sh - nb; }
 };
 
@@ -758,12 +767,12 @@ template <int RWORDS> struct ScanBits {
 template <int RWORDS> struct ScanBitsRef {
     ScanBits<RWORDS> b;
     const uint32_t *ring;
-    __device__ __forceinline__ uint64_t peek() { b.refill(ring); return b.buf; }
+    __device__ __forceinline__ uint64_t peek() { b.refill(ring); return (uint64_t)b.lo | ((uint64_t)b.mid << 32); }
     __device__ __forceinline__ void advance(uint32_t n) { b.advance(n); }
-    __device__ __forceinline__ uint64_t get(uint32_t n)
+    __device__ __forceinline__ uint64_t get(uint32_t n) /* n < 32 */
     {
         b.refill(ring);
-        const uint64_t v = b.buf & lowmask64(n);
+        const uint64_t v = b.lo & (uint32_t)lowmask64(n);
         b.advance(n);
         return v;
     }
@@ -843,10 +852,10 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     const uint32_t span = go ? (uint32_t)(mis + plen) : 0; /* the two pass path is only taken for streams far below 4 GB */
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem) + lane * LSTRIDE * 4;
     /* where this chunk picks the stream up: the reader's registers and the bands' state as the chunk before left them */
-    uint32_t *st = sstate + (size_t)(live ? tile : 0) * (6 + 2 * bands);
+    uint32_t *st = sstate + (size_t)(live ? tile : 0) * (8 + 2 * bands);
     const bool resume = !ch.first && go;
     ScanBits<RWORDS> s;
-    s.k = resume ? st[4] : 0;
+    s.k = resume ? st[5] : 0;
     uint32_t issued = s.k >> 2; /* chunks requested so far */
     auto request = [&]() {
         const uint32_t start = 16 * issued;
@@ -858,17 +867,17 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     cp_async_commit();
     cp_async_wait<0>();
     for (uint32_t c = 0; c < bands; c++) {
-        rb[c * 32 + lane] = resume ? (uint8_t)st[6 + c] : (uint8_t)0;
-        pcf[c * 32 + lane] = resume ? st[6 + bands + c] : 0u;
+        rb[c * 32 + lane] = resume ? (uint8_t)st[8 + c] : (uint8_t)0;
+        pcf[c * 32 + lane] = resume ? st[8 + bands + c] : 0u;
     }
     __syncwarp();
 
     bool failed = false;
     if (resume) {
         s.w0 = mis >> 2; s.sh = 8 * (mis & 3);
-        s.buf = (uint64_t)st[0] | ((uint64_t)st[1] << 32);
-        s.nb = st[2]; s.nxt = st[3];
-        failed = st[5] != 0;
+        s.lo = st[0]; s.mid = st[1]; s.hi = st[2];
+        s.nb = st[3]; s.nxt = st[4];
+        failed = st[6] != 0;
     }
     else s.open(ring, mis);
     const bool ftl = info.mode == M_FTL;
@@ -892,7 +901,7 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
         const uint32_t oldrung = rb[c * 32 + lane];
         const uint32_t pos = s.consumed();
         s.refill(ring);
-        const uint32_t x = (uint32_t)s.buf;
+        const uint32_t x = s.lo;
         const uint32_t idx = (x >> 1) & LMASK;
         uint32_t wl = tlen[0], wd = tdel[0];
 #pragma unroll
@@ -913,7 +922,7 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     s.refill(ring);
-                    s.advance(__byte_perm(lens, 0u, ((uint32_t)s.buf & 3) | 0x4440));
+                    s.advance(__byte_perm(lens, 0u, (s.lo & 3) | 0x4440));
                 }
             }
             else {
@@ -925,8 +934,8 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
                     for (int i = i0; i < i0 + VPR && i < 16; i++) {
                         /* selector nibbles 1..3 are zero, so bytes 1..3 of len repeat the table's first byte: junk that
                            the wrap mode shifts ignore and that cannot carry down into the sum's low byte */
-                        const uint32_t len = __byte_perm(lens, 0u, (uint32_t)s.buf & 3);
-                        s.advance_wrap(len);
+                        const uint32_t len = __byte_perm(lens, 0u, s.lo & 3);
+                        s.shift(len);
                         used += len;
                     }
                     s.nb -= used & 0xff;
@@ -956,8 +965,8 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
         a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : ST_PARSED;
     }
     else if (go) {
-        st[0] = (uint32_t)s.buf; st[1] = (uint32_t)(s.buf >> 32); st[2] = s.nb; st[3] = s.nxt; st[4] = s.k; st[5] = failed;
-        for (uint32_t c2 = 0; c2 < bands; c2++) { st[6 + c2] = rb[c2 * 32 + lane]; st[6 + bands + c2] = pcf[c2 * 32 + lane]; }
+        st[0] = s.lo; st[1] = s.mid; st[2] = s.hi; st[3] = s.nb; st[4] = s.nxt; st[5] = s.k; st[6] = failed;
+        for (uint32_t c2 = 0; c2 < bands; c2++) { st[8 + c2] = rb[c2 * 32 + lane]; st[8 + bands + c2] = pcf[c2 * 32 + lane]; }
     }
 }
 
@@ -1758,7 +1767,7 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     uint8_t *scratch = nullptr;
     keep_pool_memory();
     const size_t rec_bytes = ((size_t)a.ntiles * ngroups * sizeof(uint32_t) + 15) & ~(size_t)15,
-                 ss_bytes = (size_t)a.ntiles * (2 + 2 * a.bands) * 8, rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8;
+                 ss_bytes = (size_t)a.ntiles * ((2 + 2 * a.bands) * 8 + 32), rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8;
     cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, st);
     if (err != cudaSuccess) return err;
     uint32_t *recs = reinterpret_cast<uint32_t *>(scratch);

@@ -19,6 +19,10 @@ import sys
 import threading
 import time
 
+# many CUDA streams are in flight at once (host pipeline, two pass decode): more hardware queues than the default 8,
+# or streams share queues and wait for each other. Read when the CUDA context is created.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -219,6 +223,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-tiles", type=int, default=2048, help="tiles per end-to-end step")
+    ap.add_argument("--e2e-enc-chunk", type=int, default=128, help="tiles per chunk of the encode pipe")
+    ap.add_argument("--e2e-enc-depth", type=int, default=12, help="chunks in flight in the encode pipe")
+    ap.add_argument("--e2e-dec-chunk", type=int, default=256, help="tiles per chunk of the decode pipe")
+    ap.add_argument("--e2e-dec-depth", type=int, default=8, help="chunks in flight in the decode pipe")
     args = ap.parse_args()
     wl = args.workload
     if args.impl == "reference":
@@ -308,84 +316,72 @@ def main():
     raw_all = raw_rank * world
     value = raw_all / (ms_per_step * 1e-3) / 1e9
 
-    # end to end through the C ABI with HOST buffers: pinned host pixels -> device -> encode -> packed streams back to
-    # the host; then host streams -> device -> decode -> pixels back to the host. Every copy is inside the timed region.
-    # The batch is cut in chunks on separate CUDA streams so that copies in both directions overlap the kernels.
+    # End to end through the C ABI with HOST buffers (include/qb3cu.h, qb3cu_pipe_*): pinned host pixels ->
+    # qb3cu_pipe_encode -> packed streams + index in host memory -> qb3cu_pipe_decode -> host pixels. Every copy in
+    # either direction is inside the calls, hence inside the timed region. A step encodes one batch and decodes one
+    # batch: the encode of batch k runs on one host thread while the decode of batch k-1 (the streams the previous
+    # step produced, read from host memory) runs on another, the way a service that both ingests and serves tiles
+    # would use the library; PCIe then carries pixels up and pixels down at the same time. The same two calls made
+    # one after the other are timed as well ("sequential").
     e2e = None
     if not args.no_e2e:
         n2 = min(ntiles, args.e2e_tiles)
-        nch = 4 if n2 >= 64 else 1
-        per = (n2 + nch - 1) // nch
-        chunks = [(i * per, min(n2, (i + 1) * per)) for i in range(nch) if i * per < n2]
-        streams = [torch.cuda.Stream(device=dev) for _ in chunks]
         h_src = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
         h_src.copy_(src[:n2])
-        h_out = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
-        h_packed = [torch.empty(((b - a_) * slot,), dtype=torch.uint8).pin_memory() for a_, b in chunks]
-        h_meta = [torch.empty((2 * (b - a_) + 1,), dtype=torch.int64).pin_memory() for a_, b in chunks]
-        d_packed = [torch.empty(((b - a_) * slot,), dtype=torch.uint8, device=dev) for a_, b in chunks]
-        d_meta = [torch.empty((2 * (b - a_) + 1,), dtype=torch.int64, device=dev) for a_, b in chunks]
-        totals = [0] * len(chunks)
-        torch.cuda.synchronize()
+        h_out = torch.zeros((n2, tile_bytes), dtype=torch.uint8).pin_memory()
+        h_packed = [torch.empty((n2 * slot,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        h_off = [torch.zeros(n2, dtype=torch.int64) for _ in range(2)]
+        h_sz = [torch.zeros(n2, dtype=torch.int64) for _ in range(2)]
+        h_stat = torch.zeros(n2, dtype=torch.int32)
+        totals = [0, 0]
+        enc_pipe = q.Pipe(cfg, args.e2e_enc_chunk, args.e2e_enc_depth)
+        dec_pipe = q.Pipe(cfg, args.e2e_dec_chunk, args.e2e_dec_depth)
 
-        def e2e_step():
-            moved_h2d = moved_d2h = 0
-            # encode leg
-            for i, (a_, b) in enumerate(chunks):
-                n = b - a_
-                with torch.cuda.stream(streams[i]):
-                    src[a_:b].copy_(h_src[a_:b], non_blocking=True)
-                    q.encode_batch(cfg, src[a_:b], n, dst=dst[a_:b], sizes=sizes[a_:b], status=est[a_:b])
-                    m = d_meta[i]
-                    q.pack_streams(dst[a_:b], sizes[a_:b], n, packed=d_packed[i], offsets=m[n:2 * n], total=m[2 * n:])
-                    m[:n].copy_(sizes[a_:b], non_blocking=True)
-                    h_meta[i].copy_(m, non_blocking=True)
-                moved_h2d += n * tile_bytes
-            for i, (a_, b) in enumerate(chunks):
-                n = b - a_
-                streams[i].synchronize()   # the chunk's sizes are on the host: copy exactly the bytes it produced
-                totals[i] = int(h_meta[i][2 * n])
-                with torch.cuda.stream(streams[i]):
-                    h_packed[i][:totals[i]].copy_(d_packed[i][:totals[i]], non_blocking=True)
-                moved_d2h += totals[i] + h_meta[i].numel() * 8
-            for st_ in streams:
-                st_.synchronize()
-            # decode leg: the streams come from the host buffers
-            for i, (a_, b) in enumerate(chunks):
-                n = b - a_
-                with torch.cuda.stream(streams[i]):
-                    d_packed[i][:totals[i]].copy_(h_packed[i][:totals[i]], non_blocking=True)
-                    d_meta[i].copy_(h_meta[i], non_blocking=True)
-                    m = d_meta[i]
-                    q.decode_batch(cfg, d_packed[i], m[n:2 * n], m[:n], n, out=out[a_:b], status=dstat[a_:b])
-                    h_out[a_:b].copy_(out[a_:b], non_blocking=True)
-                moved_h2d += totals[i] + h_meta[i].numel() * 8
-                moved_d2h += n * tile_bytes
-            for st_ in streams:
-                st_.synchronize()
-            return moved_h2d, moved_d2h
+        def enc(k):
+            totals[k % 2] = enc_pipe.encode(h_src, n2, h_packed[k % 2], h_off[k % 2], h_sz[k % 2])
 
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
+        def dec(k):
+            dec_pipe.decode(h_packed[k % 2], h_off[k % 2], h_sz[k % 2], n2, h_out, h_stat)
+
+        def overlapped(k):  # encode batch k, decode batch k - 1
+            ta, tb = threading.Thread(target=enc, args=(k,)), threading.Thread(target=dec, args=(k - 1,))
+            ta.start(); tb.start(); ta.join(); tb.join()
+
+        def timed(fn, reps, k0):
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(k0, k0 + reps):
+                fn(k)
+            barrier()
+            t = (time.perf_counter() - t0) / reps
+            if world > 1:
+                tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = tt.item()
+            return t
+
+        launches_e0 = q.kernel_launches()
+        enc(0); dec(0); enc(1); dec(1)         # warm-up: buffers of both pipes reach their final size
+        overlapped(2); overlapped(3)
         k2 = max(3, args.steps // 2)
-        for _ in range(k2):
-            h2d_b, d2h_b = e2e_step()
-        barrier()
-        t_e2e = (time.perf_counter() - t0) / k2
-        if world > 1:
-            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_e2e = tt.item()
+        t_seq = timed(lambda k: (enc(k), dec(k)), k2, 4)
+        h_out.zero_()
+        t_e2e = timed(overlapped, k2, 4 + k2)
         assert wl in QUANTA or torch.equal(h_out, h_src), "end to end round trip differs"
-        assert not est[:n2].any().item() and not dstat[:n2].any().item()
+        assert not h_stat.any().item(), "tile status reports an error"
+        index_bytes = 2 * 8 * n2
+        h2d_b = n2 * tile_bytes + totals[0] + index_bytes
+        d2h_b = totals[0] + index_bytes + n2 * tile_bytes + 4 * n2
         e2e = {"value": n2 * tile_bytes * world / t_e2e / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                "tiles_per_step": n2, "ms_per_step": 1e3 * t_e2e,
-               "note": "pinned host buffers, %d chunks on %d CUDA streams; streams packed on the device "
-                       "(qb3cu_pack_streams) before the copy back" % (len(chunks), len(chunks))}
-        del h_src, h_out, h_packed, d_packed
+               "sequential": {"value": n2 * tile_bytes * world / t_seq / 1e9, "ms_per_step": 1e3 * t_seq},
+               "note": "qb3cu_pipe_encode + qb3cu_pipe_decode on pinned host buffers; a step encodes one batch and "
+                       "decodes the previous step's streams from host memory, the two calls on two host threads; "
+                       "'sequential' is the same two calls one after the other",
+               "pipes": {"encode": [args.e2e_enc_chunk, args.e2e_enc_depth], "decode": [args.e2e_dec_chunk, args.e2e_dec_depth]}}
+        enc_pipe.close(); dec_pipe.close()
+        del h_src, h_out, h_packed
         # restore the device state for anything that follows
         step()
         barrier()

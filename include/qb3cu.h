@@ -114,6 +114,50 @@ LIBQB3_EXPORT int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_stre
 LIBQB3_EXPORT int qb3cu_pack_streams(const void *d_slots, size_t slot_bytes, const uint64_t *d_sizes, void *d_packed,
                                      uint64_t *d_offsets, uint64_t *d_total, size_t ntiles, void *stream);
 
+/*
+ * ---- Host buffer pipeline: tiles in host memory in, packed streams in host memory out, and back ----
+ *
+ * What a caller of the reference does around qb3_encode / qb3_read_data for many tiles (the per image loops of
+ * cqb3.cpp:405-493 and :276-323, the tile loop of GDAL's MRF driver): here one call takes the whole batch. It is cut
+ * into chunks of tiles; host to device copies, kernels and device to host copies of different chunks overlap on
+ * several CUDA streams; streams are packed on the device so that only the bytes produced cross PCIe. A pipe owns its
+ * device staging memory, CUDA streams and pinned index buffers and keeps them between calls. One call at a time per
+ * pipe; different pipes may be used from different threads at once (an encode and a decode then share both PCIe
+ * directions). Host buffers should be page locked (qb3cu_host_alloc, cudaHostAlloc / cudaHostRegister, torch
+ * pin_memory) -- pageable memory works but is copied synchronously by the driver.
+ */
+typedef struct qb3cu_pipe qb3cu_pipe;
+
+/* chunk_tiles: tiles per chunk, 0 = chosen from the tile size (about 200 MB of pixels); depth: chunks in flight,
+   0 = default (6: a chunk's decode takes about as long as five chunks' copies). Returns NULL for bad arguments or when
+   there is no CUDA device. */
+LIBQB3_EXPORT qb3cu_pipe *qb3cu_pipe_create(const qb3cu_config *cfg, size_t chunk_tiles, int depth);
+LIBQB3_EXPORT void qb3cu_pipe_destroy(qb3cu_pipe *pipe);
+
+/*
+ * Encodes ntiles tiles from host memory (tile t at h_src + t * src_tile_pitch, laid out as for qb3cu_encode_batch).
+ * Stream t, byte identical to qb3_encode's, lands at h_packed + h_offsets[t] (16 byte aligned starts, in tile order,
+ * the first at 0) with length h_sizes[t]; *h_total = bytes of h_packed used. packed_capacity: bytes available in
+ * h_packed; ntiles * qb3cu_slot_bytes() always suffices. Returns QB3CU_ERR_PARAM when the capacity is exceeded.
+ * Synchronous: everything is in host memory on return.
+ */
+LIBQB3_EXPORT int qb3cu_pipe_encode(qb3cu_pipe *pipe, const void *h_src, size_t src_tile_pitch, void *h_packed,
+                                    size_t packed_capacity, uint64_t *h_offsets, uint64_t *h_sizes, uint64_t *h_total,
+                                    size_t ntiles);
+
+/*
+ * Decodes ntiles streams from host memory (stream t = h_lens[t] bytes at h_streams + h_offsets[t]; the layout
+ * qb3cu_pipe_encode produces, or any other with the streams of a chunk of consecutive tiles reasonably close together)
+ * into h_dst + t * dst_tile_pitch. h_status[t] = QB3CU_TILE_*. Synchronous.
+ */
+LIBQB3_EXPORT int qb3cu_pipe_decode(qb3cu_pipe *pipe, const void *h_streams, const uint64_t *h_offsets,
+                                    const uint64_t *h_lens, void *h_dst, size_t dst_tile_pitch, uint32_t *h_status,
+                                    int ref_compat, size_t ntiles);
+
+/* Page locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost). NULL on failure. */
+LIBQB3_EXPORT void *qb3cu_host_alloc(size_t bytes);
+LIBQB3_EXPORT void qb3cu_host_free(void *p);
+
 /* cudaError_t of the most recent failing CUDA call made by this library on the calling thread. */
 LIBQB3_EXPORT int qb3cu_last_cuda_error(void);
 

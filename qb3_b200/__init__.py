@@ -47,6 +47,14 @@ def lib():
         L.qb3cu_decode_batch.argtypes = [cfgp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz, vp]
         L.qb3cu_pack_streams.restype = C.c_int
         L.qb3cu_pack_streams.argtypes = [vp, sz, u64p, vp, u64p, u64p, sz, vp]
+        L.qb3cu_pipe_create.restype, L.qb3cu_pipe_create.argtypes = vp, [cfgp, sz, C.c_int]
+        L.qb3cu_pipe_destroy.restype, L.qb3cu_pipe_destroy.argtypes = None, [vp]
+        L.qb3cu_pipe_encode.restype = C.c_int
+        L.qb3cu_pipe_encode.argtypes = [vp, vp, sz, vp, sz, u64p, u64p, u64p, sz]
+        L.qb3cu_pipe_decode.restype = C.c_int
+        L.qb3cu_pipe_decode.argtypes = [vp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz]
+        L.qb3cu_host_alloc.restype, L.qb3cu_host_alloc.argtypes = vp, [sz]
+        L.qb3cu_host_free.restype, L.qb3cu_host_free.argtypes = None, [vp]
         L.qb3cu_last_cuda_error.restype, L.qb3cu_last_cuda_error.argtypes = C.c_int, []
         L.qb3cu_kernel_launches.restype, L.qb3cu_kernel_launches.argtypes = C.c_uint64, []
         _lib = L
@@ -148,6 +156,49 @@ def pack_streams(slots, sizes, ntiles, packed=None, offsets=None, total=None, st
                                   offsets.data_ptr(), total.data_ptr(), ntiles, _stream_handle(stream))
     _check(rc, "qb3cu_pack_streams")
     return packed, offsets, total
+
+
+class Pipe:
+    """qb3cu_pipe: batches held in HOST memory (numpy arrays or CPU torch tensors, ideally page locked) through the
+    device in overlapped chunks. encode() returns (total bytes used in packed); decode() fills out and status."""
+
+    def __init__(self, cfg, chunk_tiles=0, depth=0):
+        self.cfg = cfg
+        self.handle = lib().qb3cu_pipe_create(C.byref(cfg), chunk_tiles, depth)
+        if not self.handle:
+            raise RuntimeError("qb3cu_pipe_create failed: cuda=%d (there is no CPU fallback)" % lib().qb3cu_last_cuda_error())
+
+    def close(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:  # at interpreter exit the module globals may be gone already
+            _lib.qb3cu_pipe_destroy(h)
+
+    __del__ = close
+
+    @staticmethod
+    def _ptr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+
+    def encode(self, src, ntiles, packed, offsets, sizes, tile_pitch=None):
+        """src: host tiles back to back (tile_pitch bytes apart); packed: host byte buffer; offsets, sizes: host
+        uint64 / int64 arrays [ntiles]. Returns the number of bytes of packed used."""
+        ts = TYPESIZE[self.cfg.dtype]
+        if tile_pitch is None:
+            tile_pitch = (self.cfg.stride if self.cfg.stride else self.cfg.width * self.cfg.bands) * self.cfg.height * ts
+        total = C.c_uint64(0)
+        cap = packed.numel() * packed.element_size() if hasattr(packed, "numel") else packed.nbytes
+        rc = lib().qb3cu_pipe_encode(self.handle, self._ptr(src), tile_pitch, self._ptr(packed), cap, self._ptr(offsets),
+                                     self._ptr(sizes), C.addressof(total), ntiles)
+        _check(rc, "qb3cu_pipe_encode")
+        return total.value
+
+    def decode(self, packed, offsets, lens, ntiles, out, status, tile_pitch=None, ref_compat=False):
+        ts = TYPESIZE[self.cfg.dtype]
+        if tile_pitch is None:
+            tile_pitch = (self.cfg.stride if self.cfg.stride else self.cfg.width * self.cfg.bands) * self.cfg.height * ts
+        rc = lib().qb3cu_pipe_decode(self.handle, self._ptr(packed), self._ptr(offsets), self._ptr(lens), self._ptr(out),
+                                     tile_pitch, self._ptr(status), int(ref_compat), ntiles)
+        _check(rc, "qb3cu_pipe_decode")
 
 
 def shard_range(ntiles, rank, world):

@@ -3,6 +3,7 @@
  * launch geometry. No pixel or bit work happens on the host.
  */
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "qb3_device.cuh"
@@ -12,6 +13,17 @@ cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint3
 cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st, uint32_t &launches);
 cudaError_t launch_pack(const uint8_t *slots, uint64_t slot, const unsigned long long *sizes, uint8_t *packed,
                         unsigned long long *offsets, unsigned long long *total, uint32_t ntiles, cudaStream_t st);
+
+typedef void (*rows_ready_fn)(void *ctx, uint32_t row0, uint32_t row1, cudaStream_t s);
+int decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
+                      void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream,
+                      uint32_t row_chunks, rows_ready_fn rows_ready, void *rows_ctx);
+
+/* The host pipeline and the two pass decode keep many CUDA streams busy at once; with the driver's default of 8
+   hardware queues, streams share queues and wait for each other (measured: 2 x slower pipelines). The variable is read
+   when the CUDA context is created, so this only helps when the library is loaded before that -- otherwise set it in
+   the environment. An existing setting is left alone. */
+static const int g_env_once = [] { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); return 0; }();
 
 static thread_local int g_last_cuda_error = 0;
 static std::atomic<uint64_t> g_launches(0);
@@ -182,6 +194,19 @@ int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uin
                        const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch, uint32_t *d_status,
                        int ref_compat, size_t ntiles, void *stream)
 {
+    return qb3::decode_batch_rows(cfg, d_streams, d_offsets, d_lens, d_dst, dst_tile_pitch, d_status, ref_compat, ntiles,
+                                  stream, 0, nullptr, nullptr);
+}
+
+} /* extern "C" */
+
+/* qb3cu_decode_batch with the number of row chunks of the two pass decode chosen by the caller (0 = default) and a
+   hook that is told when image rows are complete (the host pipeline moves them out while the parse goes on) */
+int qb3::decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,
+                           const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch, uint32_t *d_status,
+                           int ref_compat, size_t ntiles, void *stream, uint32_t row_chunks, rows_ready_fn rows_ready,
+                           void *rows_ctx)
+{
     if (!geometry_ok(cfg) || !d_streams || !d_offsets || !d_lens || !d_dst || !d_status) return QB3CU_ERR_PARAM;
     if (ntiles == 0) return QB3CU_OK;
     if (ntiles > 0x7fffffffull) return QB3CU_ERR_PARAM;
@@ -201,11 +226,16 @@ int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uin
     a.w = cfg->width; a.h = cfg->height; a.bands = cfg->bands; a.dtype = cfg->dtype;
     a.ref_compat = ref_compat != 0;
     a.ntiles = (uint32_t)ntiles;
+    a.row_chunks = row_chunks;
+    a.rows_ready = rows_ready;
+    a.rows_ctx = rows_ctx;
     uint32_t launches = 0;
     cudaError_t err = launch_decode(a, tsize, static_cast<cudaStream_t>(stream), launches);
     count_launches(launches);
     return note_cuda(err);
 }
+
+extern "C" {
 
 int qb3cu_pack_streams(const void *d_slots, size_t slot_bytes, const uint64_t *d_sizes, void *d_packed,
                        uint64_t *d_offsets, uint64_t *d_total, size_t ntiles, void *stream)

@@ -14,6 +14,7 @@
  * per block row (QB3decode.h:730-737) and at the end (QB3decode.cpp:434-450).
  */
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 #include "qb3_device.cuh"
@@ -1717,29 +1718,55 @@ template <typename T> static cudaError_t launch_walk_any(const DecArgs &a, cudaS
                     : launch_walk<T, 16>(a, stage_blocks, stage_off, sstride, st);
 }
 
-/* The stream ordered allocator gives freed memory back to the driver at every synchronisation unless told to keep
-   it; the scratch of the next batch would then be mapped afresh, which costs more than the kernels. Once per device. */
-static void keep_pool_memory()
+/*
+ * Scratch memory of the two pass decode comes from a stream ordered pool of our own, one per device:
+ *  - it keeps what it has been given (the default is to hand freed memory back to the driver at every
+ *    synchronisation, and mapping 800 MB afresh per batch costs more than the kernels)
+ *  - it never reuses a block freed on another stream by making the new owner wait for the old one: batches decoded
+ *    concurrently on different streams must stay concurrent (they would otherwise run one after the other)
+ */
+static cudaMemPool_t scratch_pool()
 {
-    static bool done[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    done[dev] = true;
-}
-
-/* second stream of the two pass decode, one per device, made on first use */
-static cudaStream_t aux_stream()
-{
-    static cudaStream_t aux[64] = {};
+    static cudaMemPool_t pools[64] = {};
+    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!aux[dev] && cudaStreamCreateWithFlags(&aux[dev], cudaStreamNonBlocking) != cudaSuccess) aux[dev] = nullptr;
-    return aux[dev];
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) { pools[dev] = nullptr; return nullptr; }
+        uint64_t keep = ~0ull;
+        int off = 0;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolReuseAllowInternalDependencies, &off);
+    }
+    return pools[dev];
+}
+
+/* Second stream of the two pass decode: one per caller stream (a few are remembered per device), so that batches
+   decoded concurrently on different streams do not queue behind each other's rebuild kernels. */
+static cudaStream_t aux_stream(cudaStream_t user)
+{
+    struct Slot { cudaStream_t user, aux; bool used; };
+    static Slot slots[64][32] = {};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    Slot *free_slot = nullptr;
+    for (Slot &sl : slots[dev]) {
+        if (sl.used && sl.user == user) return sl.aux;
+        if (!sl.used && !free_slot) free_slot = &sl;
+    }
+    if (!free_slot) return slots[dev][0].aux; /* more caller streams than slots: share the first one's */
+    if (cudaStreamCreateWithFlags(&free_slot->aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    free_slot->user = user;
+    free_slot->used = true;
+    return free_slot->aux;
 }
 
 static int decode_chunks_override() /* QB3CU_CHUNKS=n: row chunks of the two pass decode, 1 = no pipelining */
@@ -1760,15 +1787,16 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     constexpr bool NARROW = sizeof(T) <= 2;
     typedef typename traits<T>::W W;
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
-    cudaStream_t aux = aux_stream();
-    uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : 16;
+    cudaStream_t aux = aux_stream(st);
+    uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : a.row_chunks ? a.row_chunks : 16;
     if (!aux) nchunks = 1;
     if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* at least four block rows per chunk */
     uint8_t *scratch = nullptr;
-    keep_pool_memory();
+    cudaMemPool_t pool = scratch_pool();
     const size_t rec_bytes = ((size_t)a.ntiles * ngroups * sizeof(uint32_t) + 15) & ~(size_t)15,
                  ss_bytes = (size_t)a.ntiles * ((2 + 2 * a.bands) * 8 + 32), rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8;
-    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, st);
+    cudaError_t err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, pool, st)
+                           : cudaMallocAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, st);
     if (err != cudaSuccess) return err;
     uint32_t *recs = reinterpret_cast<uint32_t *>(scratch);
     void *sstate = scratch + rec_bytes;
@@ -1821,6 +1849,12 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         rebuild_kernel<T><<<a.ntiles, threads, smem2, rst>>>(a, recs, ngroups, seg_blocks, segs, rowpitch, ch, rstate);
         err = cudaGetLastError();
         launches += 2;
+        if (err == cudaSuccess && a.rows_ready) {
+            /* the last block row of an image whose height is not a multiple of four starts at h - 4 and rewrites
+               rows of the block row before it (QB3decode.h:331-333) */
+            const uint32_t row1 = ch.last ? a.h : 4 * ch.by1, row0 = ch.last && a.h - 4 < 4 * ch.by0 ? a.h - 4 : 4 * ch.by0;
+            a.rows_ready(a.rows_ctx, row0, row1, rst);
+        }
     }
     if (nchunks > 1) { /* the caller's stream continues when the last rebuild is done */
         cudaEvent_t ev;

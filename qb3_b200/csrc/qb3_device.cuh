@@ -59,6 +59,11 @@ struct DecArgs {
     uint32_t w, h, bands, dtype;
     uint32_t ref_compat;
     uint32_t ntiles;
+    uint32_t row_chunks;  /* host side only: row chunks of the two pass decode, 0 = default */
+    /* host side only: called when the kernel that completes image rows [row0, row1) of every tile has been enqueued
+       on stream s, so that a caller can start moving them out while the rest of the batch is still being parsed */
+    void (*rows_ready)(void *ctx, uint32_t row0, uint32_t row1, cudaStream_t s);
+    void *rows_ctx;
 };
 
 /* header fields of one stream, parsed on the device */

@@ -247,3 +247,109 @@ def test_pack_streams_and_decode_packed():
         assert pk[off[t]:off[t] + sz[t]].tobytes() == dst_h[t, :sz[t]].tobytes()
     assert not st.cpu().numpy().any()
     assert np.array_equal(out.cpu().numpy().reshape(tiles.shape), tiles)
+
+
+# ------------------------------------------------------------------ host buffer pipeline (qb3cu_pipe_*)
+
+@pytest.mark.parametrize("shape,dt,mode,chunk,depth", [
+    ((37, 64, 48, 3), np.uint8, MODE_FTL, 8, 3),     # five chunks, the last one short, stages reused
+    ((10, 40, 36, 2), np.uint16, MODE_BEST, 4, 2),
+    ((5, 33, 21, 1), np.int32, MODE_BASE, 0, 0),     # default chunking: one chunk
+    ((6, 3, 50, 2), np.uint8, MODE_BASE, 4, 2),      # narrow images go through the reorder path
+    ((9, 40, 70, 3), np.uint8, MODE_BASE, 4, 2),     # several row bands per chunk, height not a multiple of four
+    ((6, 36, 130, 1), np.int16, MODE_FTL, 3, 3),
+])
+def test_pipe_host_buffers_match_oracle_and_round_trip(shape, dt, mode, chunk, depth):
+    """qb3cu_pipe_encode / qb3cu_pipe_decode: host pixels -> packed streams in host memory, byte identical to the
+    oracle's, 16 byte aligned starts in tile order; and back to the same pixels."""
+    torch_mod()
+    n, w, h, b = shape
+    tiles = synth_tiles(n, w, h, b, dt)
+    cfg = q.config(w, h, b, dtype_code(dt), mode=mode)
+    pipe = q.Pipe(cfg, chunk, depth)
+    packed = np.zeros(n * q.slot_bytes(cfg), np.uint8)
+    offsets, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    total = pipe.encode(tiles, n, packed, offsets, sizes)
+    want_off = 0
+    for t in range(n):
+        want = oracle().encode(tiles[t], mode=mode)
+        assert int(offsets[t]) == want_off and int(sizes[t]) == len(want)
+        assert packed[want_off:want_off + len(want)].tobytes() == want, "tile %d differs from the oracle" % t
+        want_off += (len(want) + 15) // 16 * 16
+    assert total == want_off
+    out = np.zeros_like(tiles)
+    status = np.full(n, 99, np.uint32)
+    pipe.decode(packed, offsets, sizes, n, out, status)
+    assert not status.any() and np.array_equal(out, tiles)
+    pipe.close()
+
+
+def test_pipe_pitched_strided_pinned_and_errors():
+    torch = torch_mod()
+    n, w, h, b = 7, 24, 20, 3
+    tiles = synth_tiles(n, w, h, b, np.uint8)
+    # tiles further apart than their size, in page locked memory
+    cfg = q.config(w, h, b, q.U8, mode=MODE_BASE)
+    pitch = tiles[0].nbytes + 100
+    h_src = torch.zeros(n * pitch, dtype=torch.uint8).pin_memory()
+    h_src.view(n, pitch)[:, :tiles[0].nbytes] = torch.from_numpy(tiles.reshape(n, -1))
+    pipe = q.Pipe(cfg, 3, 2)
+    packed = torch.zeros(n * q.slot_bytes(cfg), dtype=torch.uint8).pin_memory()
+    offsets, sizes = torch.zeros(n, dtype=torch.int64), torch.zeros(n, dtype=torch.int64)
+    pipe.encode(h_src, n, packed, offsets, sizes, tile_pitch=pitch)
+    for t in range(n):
+        o, s = int(offsets[t]), int(sizes[t])
+        assert packed[o:o + s].numpy().tobytes() == oracle().encode(tiles[t], mode=MODE_BASE)
+    h_out = torch.full((n * pitch,), 7, dtype=torch.uint8).pin_memory()
+    status = torch.zeros(n, dtype=torch.int32)
+    pipe.decode(packed, offsets, sizes, n, h_out, status, tile_pitch=pitch)
+    v = h_out.view(n, pitch).numpy()
+    assert np.array_equal(v[:, :tiles[0].nbytes].reshape(tiles.shape), tiles)
+    assert (v[:, tiles[0].nbytes:] == 7).all(), "the gap between tiles was written"
+    # too little room for the streams
+    with pytest.raises(RuntimeError):
+        pipe.encode(h_src, n, packed[:int(offsets[3])], offsets, sizes, tile_pitch=pitch)
+    # a damaged stream is reported per tile, its neighbours decode
+    bad = packed.clone()
+    bad[int(offsets[2])] = 0
+    pipe.decode(bad, offsets, sizes, n, h_out, status, tile_pitch=pitch)
+    assert status.tolist() == [0, 0, q.TILE_BAD_HEADER, 0, 0, 0, 0]
+    pipe.close()
+    # lines further apart than their length
+    stride = w * b + 5
+    cfg2 = q.config(w, h, b, q.U8, mode=MODE_FTL, stride=stride)
+    buf = np.full((n, h, stride), 9, np.uint8)
+    buf[:, :, :w * b] = tiles.reshape(n, h, w * b)
+    pipe2 = q.Pipe(cfg2, 4, 2)
+    packed2 = np.zeros(n * q.slot_bytes(cfg2), np.uint8)
+    off2, sz2 = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    pipe2.encode(buf, n, packed2, off2, sz2)
+    for t in range(n):
+        assert packed2[int(off2[t]):int(off2[t] + sz2[t])].tobytes() == oracle().encode(tiles[t], mode=MODE_FTL)
+    out2 = np.full_like(buf, 5)
+    st2 = np.zeros(n, np.uint32)
+    pipe2.decode(packed2, off2, sz2, n, out2, st2)
+    assert not st2.any() and np.array_equal(out2[:, :, :w * b], buf[:, :, :w * b]) and (out2[:, :, w * b:] == 5).all()
+    pipe2.close()
+
+
+def test_pipe_rle_and_stored_tiles():
+    """Tiles the two pass decode leaves to the kernels after it (RLE streams, stored tiles) travel back whole."""
+    torch_mod()
+    n, w, h, b = 8, 64, 72, 1
+    tiles = synth_tiles(n, w, h, b, np.uint8)
+    tiles[1] = 0                                                        # RLE pays: mode byte 7
+    tiles[4] = np.random.default_rng(5).integers(0, 256, tiles[4].shape, dtype=np.uint8)   # incompressible: stored
+    cfg = q.config(w, h, b, q.U8, mode=MODE_BEST)
+    pipe = q.Pipe(cfg, 8, 2)
+    packed = np.zeros(n * q.slot_bytes(cfg), np.uint8)
+    offsets, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    pipe.encode(tiles, n, packed, offsets, sizes)
+    for t in range(n):
+        assert packed[int(offsets[t]):int(offsets[t] + sizes[t])].tobytes() == oracle().encode(tiles[t], mode=MODE_BEST)
+    assert packed[int(offsets[1]) + 10] == 7 and packed[int(offsets[4]) + 10] == 255
+    out = np.zeros_like(tiles)
+    status = np.full(n, 99, np.uint32)
+    pipe.decode(packed, offsets, sizes, n, out, status)
+    assert not status.any() and np.array_equal(out, tiles)
+    pipe.close()

@@ -454,42 +454,49 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
 
             const bool active = tid < ng;
             W m[16];
+            uint32_t mw[6], ml[6]; /* 8 bit data, table path: the sixteen codes merged three to a word, and the words' lengths */
             W bitsused = 0;
             uint32_t rung = 0;
             if (active) {
                 const uint32_t bx = bx0 + blk, x0 = min(4 * bx, a.vw - 4), cb = a.cband[c];
+                /* where row r of the segment starts in the staging buffer: rows keep their source alignment, so the
+                   offset moves with the row's address modulo 16. One 64 bit address is worked out, the rest follows. */
                 uint32_t rowoff[4];
+                {
+                    uint32_t mis = 0, step = 0;
+                    if (a.vec_stage) {
+                        mis = (uint32_t)((uintptr_t)(src + ((uint64_t)y0 * a.stride + (uint64_t)xs * a.bands) * sizeof(T)) & 15);
+                        step = (uint32_t)(a.stride * sizeof(T)) & 15;
+                    }
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    uint32_t mis = 0;
-                    if (a.vec_stage)
-                        mis = (uint32_t)((uintptr_t)(src + ((uint64_t)(y0 + r) * a.stride + (uint64_t)xs * a.bands) * sizeof(T)) & 15);
-                    rowoff[r] = r * a.rowpitch + mis;
+                    for (int r = 0; r < 4; r++) rowoff[r] = r * a.rowpitch + ((mis + r * step) & 15);
                 }
                 const W TM = (W)lowmask64(BITS);
-                const bool derived = cb != c;
-                /* per row: this block's first pixel, own band and core band */
-                const T *own[4], *core[4];
+                /* the core band is always read and masked away for a band that is its own core: the lanes of a warp
+                   hold different bands, and a branch here would run the whole gather twice */
+                const W dmask = cb != c ? TM : (W)0;
+                /* per row: this block's first pixel, own band; the core band is a fixed distance away */
+                const T *own[4];
+                const int core_d = (int)cb - (int)c;
+                uint32_t coloff[4];
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    const T *p = reinterpret_cast<const T *>(sbuf + rowoff[r]) + (x0 - xs) * a.bands;
-                    own[r] = p + c;
-                    core[r] = p + cb;
+                    own[r] = reinterpret_cast<const T *>(sbuf + rowoff[r]) + (x0 - xs) * a.bands + c;
+                    coloff[r] = r * a.bands;
                 }
                 W prv;
                 if (blk > 0) { /* last value of the previous block: curve position 15 */
                     const uint32_t n15 = curve_pos<CURVE>(a.order, 15);
                     const int back = (int)((4 * (bx - 1) + (n15 & 3)) - x0) * (int)a.bands;
-                    prv = (W)own[n15 >> 2][back];
-                    if (derived) prv = (prv - (W)core[n15 >> 2][back]) & TM;
+                    const T *q15 = own[n15 >> 2] + back;
+                    prv = ((W)q15[0] - ((W)q15[core_d] & dmask)) & TM;
                 }
                 else prv = (W)carry_prev[par * a.bands + c] & TM;
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const uint32_t n = curve_pos<CURVE>(a.order, i);
-                    const uint32_t px = (n & 3) * a.bands;
-                    W v = (W)own[n >> 2][px];
-                    if (derived) v = (v - (W)core[n >> 2][px]) & TM;
+                    const T *q = own[n >> 2] + coloff[n & 3];
+                    const W v = ((W)q[0] - ((W)q[core_d] & dmask)) & TM;
                     m[i] = mags<BITS, W>(v - prv);
                     prv = v;
                     bitsused |= m[i];
@@ -534,8 +541,26 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
 #pragma unroll
                             for (int i = 0; i < 16; i++) m[i] = (W)packed_code32((uint32_t)m[i], rung);
                         }
+                        if (BITS == 8) {
+                            /* codes are 9 bits at most: three of them travel as one word of up to 27 bits. m[0..5] become
+                               the merged words, m[8..13] their lengths */
 #pragma unroll
-                        for (int i = 0; i < 16; i++) len += (uint32_t)m[i] >> 20;
+                            for (int j = 0; j < 6; j++) {
+                                const uint32_t a0 = (uint32_t)m[3 * j], l0 = a0 >> 20;
+                                uint32_t cw = a0 & 0xfffffu, cl = l0;
+                                if (j < 5) {
+                                    const uint32_t a1 = (uint32_t)m[3 * j + 1], a2 = (uint32_t)m[3 * j + 2], l01 = l0 + (a1 >> 20);
+                                    cw |= ((a1 & 0xfffffu) << l0) | ((a2 & 0xfffffu) << l01);
+                                    cl = l01 + (a2 >> 20);
+                                }
+                                mw[j] = cw; ml[j] = cl;
+                                len += cl;
+                            }
+                        }
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) len += (uint32_t)m[i] >> 20;
+                        }
                     }
                     else {
                         prepare_group<W>(m, rung, use_step);
@@ -680,9 +705,16 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
                     }
                     pk.put32(b, bitsused ? 17 : 1);
                 }
-                else if (USE_LUT) {
+                else if (USE_LUT && BITS == 8) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) pk.put32((uint32_t)m[i] & 0xfffffu, (uint32_t)m[i] >> 20);
+                    for (int j = 0; j < 6; j++) pk.put32(mw[j], ml[j]);
+                }
+                else if (USE_LUT) { /* 16 bit data: codes of up to 17 bits go in pairs */
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const uint32_t a0 = (uint32_t)m[i], a1 = (uint32_t)m[i + 1], l0 = a0 >> 20;
+                        pk.put64((uint64_t)(a0 & 0xfffffu) | ((uint64_t)(a1 & 0xfffffu) << l0), l0 + (a1 >> 20));
+                    }
                 }
                 else {
 #pragma unroll

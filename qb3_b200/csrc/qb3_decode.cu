@@ -713,6 +713,14 @@ struct RowChunk {
     uint32_t first, last;
 };
 
+/* How a scan launch is laid out: several warps to a CTA, each with its own slice of shared memory; and whether the
+   launch walks its block rows as 'inner' sub-chunks, reporting each at flags[j]. */
+struct ScanPlan {
+    uint32_t warp_smem; /* bytes of shared memory per warp, multiple of 16 */
+    uint32_t inner;     /* >= 1 */
+    uint32_t *flags;    /* null, or inner counters */
+};
+
 /*
  * Bit buffer of scan_kernel: one stream per lane. 64 bits of look-ahead in registers, fed a 32 bit word at a time from
  * the lane's own ring in shared memory, one word of read-ahead. The ring is filled by cp.async in 16 byte chunks,
@@ -795,8 +803,8 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void 
  * rebuild_kernel then decodes all groups of a tile in parallel.
  */
 template <typename T>
-__global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
-                                                     const RowChunk ch, uint32_t *__restrict__ sstate)
+__global__ void __launch_bounds__(128, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
+                                                      const RowChunk ch, uint32_t *__restrict__ sstate, const ScanPlan plan)
 {
     typedef uint32_t W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -810,8 +818,10 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     constexpr int NTW = (2 << U) / 8;            /* 32 bit words of a 4 bit per entry switch table */
     static_assert(4 * (AHEAD - 1) >= 2 * EVERY * GWORDS + 4, "ring too small for two upkeep intervals");
 
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x, bands = a.bands;
+    extern __shared__ __align__(16) uint8_t smem_cta[];
+    const uint32_t lane = threadIdx.x & 31, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), bands = a.bands;
+    if (wid * 32 >= a.ntiles) return; /* warps are on their own: no CTA wide barrier anywhere in this kernel */
+    uint8_t *smem = smem_cta + (threadIdx.x >> 5) * plan.warp_smem;
     const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
     uint8_t *rb = smem + 32 * LSTRIDE * 4;                          /* [band][lane] running rung */
     uint32_t *pcf = reinterpret_cast<uint32_t *>(rb + 32 * bands);  /* [band][lane] last common factor */
@@ -830,7 +840,7 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
         }
     }
 
-    const uint32_t tile = blockIdx.x * 32 + lane;
+    const uint32_t tile = wid * 32 + lane;
     const bool live = tile < a.ntiles;
     const uint8_t *stream = nullptr;
     uint64_t slen = 0;
@@ -884,8 +894,13 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
     const bool ftl = info.mode == M_FTL;
     uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
 
-    const uint32_t per_row = ((a.w + 3) / 4) * bands, g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
+    const uint32_t per_row = ((a.w + 3) / 4) * bands;
     uint32_t c = 0, upkeep = 1;
+    /* plan.inner > 1: this launch walks all the row chunks itself and counts a warp in at flags[j] when its streams
+       are through chunk j; the host has queued the rebuild of chunk j behind a wait on that counter */
+    for (uint32_t j = 0; j < plan.inner; j++) {
+    const uint32_t g_begin = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * j / plan.inner)) * per_row,
+                   g_end = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * (j + 1) / plan.inner)) * per_row;
     for (uint32_t g = g_begin; g < g_end; g++) {
         /* ring upkeep every few groups: request chunks up to AHEAD beyond the one being read. What was requested one
            upkeep ago has had EVERY groups to land and is waited for; the new requests are for reads two upkeeps away. */
@@ -959,6 +974,12 @@ __global__ void __launch_bounds__(32, 1) scan_kernel(const DecArgs a, uint32_t *
         if (go) rec[g] = (pos << 4) | r;
         c = c + 1 == bands ? 0 : c + 1;
     }
+    if (plan.flags) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(plan.flags + j, 1u);
+    }
+    }
     cp_async_wait<0>();
     if (go && ch.last) {
         const uint64_t total = 8 * plen, used = s.consumed();
@@ -1003,8 +1024,9 @@ template <int RWORDS> struct RingBits {
  * eighth of the groups per byte of the 8 bit case, so the per group cost matters that much less.
  */
 template <typename T>
-__global__ void __launch_bounds__(32, 1) scan_wide_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
-                                                          const RowChunk ch, unsigned long long *__restrict__ sstate)
+__global__ void __launch_bounds__(128, 1) scan_wide_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
+                                                           const RowChunk ch, unsigned long long *__restrict__ sstate,
+                                                           const ScanPlan plan)
 {
     typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -1016,8 +1038,10 @@ __global__ void __launch_bounds__(32, 1) scan_wide_kernel(const DecArgs a, uint3
     constexpr int AHEAD = RWORDS / 4 - 2;
     static_assert(4 * (AHEAD - 1) >= 2 * EVERY * GWORDS + 4, "ring too small for two upkeep intervals");
 
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x, bands = a.bands;
+    extern __shared__ __align__(16) uint8_t smem_cta[];
+    const uint32_t lane = threadIdx.x & 31, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), bands = a.bands;
+    if (wid * 32 >= a.ntiles) return;
+    uint8_t *smem = smem_cta + (threadIdx.x >> 5) * plan.warp_smem;
     const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
     W *pcf = reinterpret_cast<W *>(smem + 32 * LSTRIDE * 4);              /* [band][lane] last common factor */
     uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + 32 * bands);           /* [band][lane] running rung */
@@ -1025,7 +1049,7 @@ __global__ void __launch_bounds__(32, 1) scan_wide_kernel(const DecArgs a, uint3
     uint16_t *dsw = reinterpret_cast<uint16_t *>(cbs + 32 * bands + ((32 * bands) & 1)); /* rung switch decode table */
     for (uint32_t i = lane; i < (2u << U); i += 32) dsw[i] = (uint16_t)ds_entry(U, i);
 
-    const uint32_t tile = blockIdx.x * 32 + lane;
+    const uint32_t tile = wid * 32 + lane;
     const bool live = tile < a.ntiles;
     const uint8_t *stream = nullptr;
     uint64_t slen = 0;
@@ -1070,8 +1094,11 @@ __global__ void __launch_bounds__(32, 1) scan_wide_kernel(const DecArgs a, uint3
 
     const bool ftl = info.mode == M_FTL;
     uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
-    const uint32_t per_row = ((a.w + 3) / 4) * bands, g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
+    const uint32_t per_row = ((a.w + 3) / 4) * bands;
     uint32_t c = 0, upkeep = 1;
+    for (uint32_t j = 0; j < plan.inner; j++) { /* see scan_kernel */
+    const uint32_t g_begin = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * j / plan.inner)) * per_row,
+                   g_end = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * (j + 1) / plan.inner)) * per_row;
     for (uint32_t g = g_begin; g < g_end; g++) {
         if (--upkeep == 0) {
             upkeep = EVERY;
@@ -1113,6 +1140,12 @@ __global__ void __launch_bounds__(32, 1) scan_wide_kernel(const DecArgs a, uint3
         rb[c * 32 + lane] = (uint8_t)r;
         if (go) rec[g] = (pos << 6) | r;
         c = c + 1 == bands ? 0 : c + 1;
+    }
+    if (plan.flags) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(plan.flags + j, 1u);
+    }
     }
     cp_async_wait<0>();
     if (go && ch.last) {
@@ -1747,25 +1780,30 @@ static cudaMemPool_t scratch_pool()
     return pools[dev];
 }
 
-/* Second stream of the two pass decode: one per caller stream (a few are remembered per device), so that batches
-   decoded concurrently on different streams do not queue behind each other's rebuild kernels. */
-static cudaStream_t aux_stream(cudaStream_t user)
+/* Second stream of the two pass decode: one per caller stream and kind (a few are remembered per device), so that
+   batches decoded concurrently on different streams do not queue behind each other's kernels. high: with the highest
+   priority, for scans that run on SMs of their own; else of default priority, for rebuilds beside scans. */
+static cudaStream_t aux_stream(cudaStream_t user, bool high)
 {
-    struct Slot { cudaStream_t user, aux; bool used; };
-    static Slot slots[64][32] = {};
+    struct Slot { cudaStream_t user, aux; bool used, high; };
+    static Slot slots[64][64] = {};
     static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
-    Slot *free_slot = nullptr;
+    Slot *free_slot = nullptr, *same_kind = nullptr;
     for (Slot &sl : slots[dev]) {
-        if (sl.used && sl.user == user) return sl.aux;
+        if (sl.used && sl.user == user && sl.high == high) return sl.aux;
+        if (sl.used && sl.high == high && !same_kind) same_kind = &sl;
         if (!sl.used && !free_slot) free_slot = &sl;
     }
-    if (!free_slot) return slots[dev][0].aux; /* more caller streams than slots: share the first one's */
-    if (cudaStreamCreateWithFlags(&free_slot->aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (!free_slot) return same_kind ? same_kind->aux : nullptr; /* more caller streams than slots: share one */
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&free_slot->aux, cudaStreamNonBlocking, high ? greatest : least) != cudaSuccess) return nullptr;
     free_slot->user = user;
     free_slot->used = true;
+    free_slot->high = high;
     return free_slot->aux;
 }
 
@@ -1787,24 +1825,51 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     constexpr bool NARROW = sizeof(T) <= 2;
     typedef typename traits<T>::W W;
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
-    cudaStream_t aux = aux_stream(st);
     uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : a.row_chunks ? a.row_chunks : 16;
-    if (!aux) nchunks = 1;
     if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* at least four block rows per chunk */
+    /*
+     * The scans run chunk after chunk on a stream of our own with the highest priority, the rebuilds on the caller's
+     * stream, each behind the scan of its chunk. When the batch leaves most SMs unused by the scan, its CTAs (four warps,
+     * one per warp scheduler) ask for a whole SM's shared memory, so that no rebuild CTA is ever co-resident with them:
+     * the serial parse is latency bound, and sharing its warp schedulers with the rebuild's warps costs it 15 %
+     * (measured). The priority makes the next chunk's scan CTAs take the SMs the last one's just left before the
+     * rebuild's thousands of CTAs get there.
+     */
     uint8_t *scratch = nullptr;
     cudaMemPool_t pool = scratch_pool();
     const size_t rec_bytes = ((size_t)a.ntiles * ngroups * sizeof(uint32_t) + 15) & ~(size_t)15,
-                 ss_bytes = (size_t)a.ntiles * ((2 + 2 * a.bands) * 8 + 32), rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8;
-    cudaError_t err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, pool, st)
-                           : cudaMallocAsync(reinterpret_cast<void **>(&scratch), rec_bytes + ss_bytes + rs_bytes, st);
+                 ss_bytes = (size_t)a.ntiles * ((2 + 2 * a.bands) * 8 + 32), rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8,
+                 total_bytes = rec_bytes + ss_bytes + rs_bytes;
+    cudaError_t err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), total_bytes, pool, st)
+                           : cudaMallocAsync(reinterpret_cast<void **>(&scratch), total_bytes, st);
     if (err != cudaSuccess) return err;
     uint32_t *recs = reinterpret_cast<uint32_t *>(scratch);
     void *sstate = scratch + rec_bytes;
     unsigned long long *rstate = reinterpret_cast<unsigned long long *>(scratch + rec_bytes + ss_bytes);
 
     constexpr int RWORDS = sizeof(T) == 1 ? 64 : sizeof(T) == 2 ? 128 : 256;
-    const size_t smem1 = NARROW ? (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6
-                                : (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * (sizeof(W) + 2) + 2 + 2 * (2u << traits<T>::U);
+    size_t smem1 = NARROW ? (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6
+                          : (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * (sizeof(W) + 2) + 2 + 2 * (2u << traits<T>::U);
+    smem1 = (smem1 + 15) & ~(size_t)15;
+    /* Scan CTAs: four warps (one per warp scheduler of an SM) with the SM's whole shared memory when that leaves two
+       thirds of the SMs to the rebuild; else a warp per CTA, spread over the SMs and sharing them with the rebuild. */
+    const uint32_t nwarps = (a.ntiles + 31) / 32;
+    int dev = 0, nsm = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    /* four warps to an SM only for 8 bit data: with the longer rings of the other types that many copies in flight per
+       SM slow each other down (measured: 16 bit scans take 1.8 times as long four to an SM) */
+    uint32_t wpc = getenv("QB3CU_SCAN_WPC") ? (uint32_t)atoi(getenv("QB3CU_SCAN_WPC")) : sizeof(T) == 1 ? 4 : 1;
+    while (wpc > 1 && wpc * smem1 > (size_t)smem_max) wpc >>= 1;
+    const bool own_sm = nchunks > 1 && !a.shared_sm && (int)((nwarps + wpc - 1) / wpc) * 3 <= nsm && !getenv("QB3CU_SCAN_SHARED_SM");
+    if (!own_sm) wpc = 1;
+    cudaStream_t aux = nchunks > 1 ? aux_stream(st, own_sm) : nullptr;
+    if (nchunks > 1 && !aux) { cudaFreeAsync(scratch, st); return cudaErrorUnknown; }
+    if (wpc > nwarps) wpc = nwarps;
+    const uint32_t scan_ctas = (nwarps + wpc - 1) / wpc;
+    const size_t scan_smem = own_sm ? (size_t)smem_max : wpc * smem1;
+
     /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
     const uint32_t max_threads = NARROW ? 384 : 256; /* what rebuild_kernel is built for */
     uint32_t seg_blocks = max_threads / a.bands;
@@ -1820,11 +1885,28 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         static const size_t pad = [] { const char *e = getenv("QB3CU_RB_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
         if (pad > smem2) smem2 = pad;
     }
-    if constexpr (NARROW) err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    else err = cudaFuncSetAttribute(scan_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if constexpr (NARROW) err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+    else err = cudaFuncSetAttribute(scan_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
 
-    cudaStream_t rst = nchunks > 1 ? aux : st;
+    /* With SMs of their own the scans go to our high priority stream and the rebuilds stay on the caller's. Without,
+       the scans stay on the caller's stream, back to back, and the rebuilds go to the second stream: a scan launched
+       while a rebuild's CTAs are still being handed out gets its small CTAs packed onto the few SMs with room, many
+       warps to a scheduler, and runs four times slower (measured); following its predecessor in the same stream it
+       gets in before the rebuild that waits on an event. */
+    cudaStream_t sst = nchunks > 1 && own_sm ? aux : st, rst = nchunks > 1 && !own_sm ? aux : st;
+    auto order_after = [&](cudaStream_t later, cudaStream_t earlier) { /* later waits for what earlier holds now */
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        e = cudaEventRecord(ev, earlier);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(later, ev, 0);
+        cudaEventDestroy(ev);
+        return e;
+    };
+    if (err == cudaSuccess && nchunks > 1) err = order_after(aux, st); /* the streams and the scratch memory are ready */
+    ScanPlan plan;
+    plan.warp_smem = (uint32_t)smem1; plan.inner = 1; plan.flags = nullptr;
     for (uint32_t i = 0; i < nchunks && err == cudaSuccess; i++) {
         RowChunk ch;
         ch.by0 = (uint32_t)((uint64_t)nby * i / nchunks);
@@ -1832,20 +1914,13 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         ch.first = i == 0;
         ch.last = i + 1 == nchunks;
         if constexpr (NARROW)
-            scan_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups, ch, static_cast<uint32_t *>(sstate));
+            scan_kernel<T><<<scan_ctas, 32 * wpc, scan_smem, sst>>>(a, recs, ngroups, ch, static_cast<uint32_t *>(sstate), plan);
         else
-            scan_wide_kernel<T><<<(a.ntiles + 31) / 32, 32, smem1, st>>>(a, recs, ngroups, ch, static_cast<unsigned long long *>(sstate));
+            scan_wide_kernel<T><<<scan_ctas, 32 * wpc, scan_smem, sst>>>(a, recs, ngroups, ch,
+                                                                         static_cast<unsigned long long *>(sstate), plan);
         err = cudaGetLastError();
+        if (err == cudaSuccess && nchunks > 1) err = order_after(rst, sst);
         if (err != cudaSuccess) break;
-        if (nchunks > 1) {
-            cudaEvent_t ev;
-            err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-            if (err != cudaSuccess) break;
-            err = cudaEventRecord(ev, st);
-            if (err == cudaSuccess) err = cudaStreamWaitEvent(rst, ev, 0);
-            cudaEventDestroy(ev);
-            if (err != cudaSuccess) break;
-        }
         rebuild_kernel<T><<<a.ntiles, threads, smem2, rst>>>(a, recs, ngroups, seg_blocks, segs, rowpitch, ch, rstate);
         err = cudaGetLastError();
         launches += 2;
@@ -1856,14 +1931,8 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
             a.rows_ready(a.rows_ctx, row0, row1, rst);
         }
     }
-    if (nchunks > 1) { /* the caller's stream continues when the last rebuild is done */
-        cudaEvent_t ev;
-        cudaError_t e2 = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e2 == cudaSuccess) {
-            e2 = cudaEventRecord(ev, rst);
-            if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, ev, 0);
-            cudaEventDestroy(ev);
-        }
+    if (rst != st) { /* the caller's stream continues when the last rebuild is done */
+        const cudaError_t e2 = order_after(st, rst);
         if (err == cudaSuccess) err = e2;
     }
     const cudaError_t ferr = cudaFreeAsync(scratch, st);

@@ -71,18 +71,20 @@ __device__ __forceinline__ void stage_rows(const EncArgs &a, const uint8_t *src,
     const uint32_t rowvals = npix * a.bands;
     if (a.vec_stage) {
         const uint32_t rowbytes = rowvals * (uint32_t)sizeof(T), upr = a.rowpitch >> 4;
+        const uint64_t lpitch = a.stride * sizeof(T);
+        const uint8_t *g0 = src + ((uint64_t)y0 * a.stride + (uint64_t)xs * a.bands) * sizeof(T);
         for (uint32_t idx = threadIdx.x; idx < 4 * upr; idx += blockDim.x) {
-            const uint32_t r = idx / upr, u = idx - r * upr;
-            const uint8_t *g = src + ((uint64_t)(y0 + r) * a.stride + (uint64_t)xs * a.bands) * sizeof(T);
-            const uint32_t mis = (uint32_t)((uintptr_t)g & 15);
-            if (u >= ((mis + rowbytes + 15) >> 4)) continue;
-            const uint8_t *ga = g - mis + 16 * (size_t)u;
-            uint8_t *sa = stage + r * a.rowpitch + 16 * u;
-            if (ga >= g && ga + 16 <= g + rowbytes)
+            const uint32_t r = (idx >= upr) + (idx >= 2 * upr) + (idx >= 3 * upr), u = idx - r * upr;
+            const uint8_t *g = g0 + r * lpitch;
+            const uint32_t mis = (uint32_t)((uintptr_t)g & 15), first = 16 * u; /* first: offset in the row's aligned span */
+            if (first >= mis + rowbytes) continue;
+            const uint8_t *ga = g - mis + first;
+            uint8_t *sa = stage + r * a.rowpitch + first;
+            if (first >= mis && first + 16 <= mis + rowbytes)
                 cp_async16(sa, ga);
             else
-                for (int b = 0; b < 16; b++)
-                    if (ga + b >= g && ga + b < g + rowbytes) sa[b] = ga[b];
+                for (uint32_t b = 0; b < 16; b++)
+                    if (first + b >= mis && first + b < mis + rowbytes) sa[b] = ga[b];
         }
         return;
     }

@@ -183,12 +183,8 @@ qb3cu_pipe *qb3cu_pipe_create(const qb3cu_config *cfg, size_t chunk_tiles, int d
     p->depth = depth ? (size_t)(depth < 2 ? 2 : depth) : 6; /* a chunk is collected while the next one uploads: two at least */
     p->stages.resize(p->depth);
     bool ok = true;
-    /* The stage streams run the serial parse of a decode, whose few warps are the critical path: they get the highest
-       priority, so that their thread blocks never queue behind the thousands of a rebuild or an encode. */
-    int least = 0, greatest = 0;
-    cudaDeviceGetStreamPriorityRange(&least, &greatest);
     for (Stage &s : p->stages) {
-        ok = ok && note_cuda(cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, greatest)) == QB3CU_OK
+        ok = ok && note_cuda(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) == QB3CU_OK
                 && note_cuda(cudaStreamCreateWithFlags(&s.out, cudaStreamNonBlocking)) == QB3CU_OK
                 && note_cuda(cudaEventCreateWithFlags(&s.index_ready, cudaEventDisableTiming)) == QB3CU_OK
                 && note_cuda(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming)) == QB3CU_OK

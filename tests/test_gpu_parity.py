@@ -353,3 +353,63 @@ def test_pipe_rle_and_stored_tiles():
     pipe.decode(packed, offsets, sizes, n, out, status)
     assert not status.any() and np.array_equal(out, tiles)
     pipe.close()
+
+
+# ------------------------------------------------------------------ cqb3cu, the command line tool
+
+def _write_pnm(path, img):
+    h, w, b = img.shape
+    big = img.astype(">u2") if img.dtype == np.uint16 else img
+    with open(path, "wb") as f:
+        f.write(b"P%d\n%d %d\n%d\n" % (5 if b == 1 else 6, w, h, 65535 if img.dtype == np.uint16 else 255))
+        f.write(big.tobytes())
+
+
+def test_cli_encode_decode_bandmix_and_folder(tmp_path):
+    """cqb3cu with the reference tool's options: streams byte identical to the oracle for the same settings, PNM and
+    raw round trips, -m x = the smallest of the ten band maps, folder mode through the batched pipeline."""
+    import subprocess
+    torch_mod()
+    exe = os.path.join(os.path.dirname(PRODUCT_SO), "..", "apps", "cqb3cu")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "-C", os.path.dirname(exe)], check=True)
+    rgb = synth_tiles(3, 70, 50, 3, np.uint8)
+    gray16 = synth_tiles(1, 37, 41, 1, np.uint16)[0]
+    p = str(tmp_path / "a.ppm")
+    _write_pnm(p, rgb[0])
+    run = lambda *a: subprocess.run([exe, *a], capture_output=True, text=True, cwd=str(tmp_path))
+    # default (BASE), -b (BEST), -f (FTL), -q 3, explicit band map
+    for flags, kw in (([], dict(mode=MODE_BASE)), (["-b"], dict(mode=MODE_BEST)), (["-f"], dict(mode=MODE_FTL)),
+                      (["-q", "3"], dict(mode=MODE_BASE, quanta=3)), (["-m", "0,0,2"], dict(mode=MODE_BASE, cband=[0, 0, 2]))):
+        r = run(*flags, p, "o.qb3")
+        assert r.returncode == 0, r
+        assert (tmp_path / "o.qb3").read_bytes() == oracle().encode(rgb[0], **kw), flags
+    # decode back to PNM
+    r = run("-f", p, "f.qb3"); assert r.returncode == 0
+    r = run("-d", "f.qb3", "back.ppm"); assert r.returncode == 0, r
+    assert (tmp_path / "back.ppm").read_bytes() == (tmp_path / "a.ppm").read_bytes()
+    # 16 bit gray through PNM, int32 through raw
+    _write_pnm(str(tmp_path / "g.pgm"), gray16)
+    assert run("-b", "g.pgm", "g.qb3").returncode == 0
+    assert (tmp_path / "g.qb3").read_bytes() == oracle().encode(gray16, mode=MODE_BEST)
+    i32 = synth_tiles(1, 21, 9, 2, np.int32)[0]
+    (tmp_path / "i.raw").write_bytes(i32.tobytes())
+    assert run("-s", "21x9x2:i32", "i.raw", "i.qb3").returncode == 0
+    assert (tmp_path / "i.qb3").read_bytes() == oracle().encode(i32, mode=MODE_BASE)
+    assert run("-d", "-s", "21x9x2:i32", "i.qb3", "i2.raw").returncode == 0
+    assert (tmp_path / "i2.raw").read_bytes() == i32.tobytes()
+    # band mix search: the smallest of the reference's ten maps, the first one on ties
+    combos = [[1, 1, 1], [0, 0, 0], [0, 0, 2], [0, 1, 0], [0, 1, 1], [0, 1, 2], [0, 2, 2], [1, 1, 2], [2, 1, 2], [2, 2, 2]]
+    streams = [oracle().encode(rgb[0], mode=MODE_BASE, cband=c) for c in combos]
+    best = min(range(10), key=lambda k: (len(streams[k]), k))
+    assert run("-m", "x", p, "x.qb3").returncode == 0
+    assert (tmp_path / "x.qb3").read_bytes() == streams[best]
+    # folder mode
+    d = tmp_path / "in"; d.mkdir(); o = tmp_path / "out"; o.mkdir()
+    for t in range(3):
+        _write_pnm(str(d / ("t%d.ppm" % t)), rgb[t])
+    _write_pnm(str(d / "g.pgm"), gray16)
+    r = run("-f", str(d), str(o)); assert r.returncode == 0, r
+    for t in range(3):
+        assert (o / ("t%d.qb3" % t)).read_bytes() == oracle().encode(rgb[t], mode=MODE_FTL)
+    assert (o / "g.qb3").read_bytes() == oracle().encode(gray16, mode=MODE_FTL)

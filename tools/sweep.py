@@ -1,0 +1,72 @@
+"""Throughput sweep (BASELINE config 5): tile size x bands x type x mode at about 1 GB of raw pixels per
+case on one GPU, kernels only (inputs resident in HBM). Prints a markdown table; every case is round trip checked.
+
+  python tools/sweep.py [--gb 1.0] [--quick] > profiles/r01_sweep.md
+"""
+import argparse, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import qb3_b200 as q
+from bench import device_synth_tiles
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--gb", type=float, default=1.0)
+ap.add_argument("--quick", action="store_true")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+NAMES = ["u8", "i8", "u16", "i16", "u32", "i32", "u64", "i64"]
+MODES = [(8, "FTL"), (4, "BASE"), (7, "BEST")]
+cases = []
+# tile size sweep on 3 band u8 and 1 band u16
+for side in (64, 128, 256, 512, 1024, 2048, 4096):
+    cases.append((side, side, 3, 0))
+    if not args.quick:
+        cases.append((side, side, 1, 2))
+# band sweep on 256 x 256
+for b in (1, 4, 8, 16, 64, 256):
+    cases.append((256, 256, b, 0))
+    if not args.quick:
+        cases.append((256, 256, b, 2))
+# type sweep on 512 x 512 x 1
+for dt in range(8):
+    cases.append((512, 512, 1, dt))
+seen = set()
+print("| tile | bands | type | mode | tiles | ratio | encode ms | decode ms | encode GB/s | decode GB/s | enc+dec GB/s |")
+print("|---|---|---|---|---|---|---|---|---|---|---|")
+for w, h, b, dt in cases:
+    for mode, mname in MODES:
+        if (w, h, b, dt, mode) in seen:
+            continue
+        seen.add((w, h, b, dt, mode))
+        if args.quick and mode == 7 and (w > 1024 or b > 16):
+            continue
+        ts = q.TYPESIZE[dt]
+        tile = w * h * b * ts
+        n = max(1, int(args.gb * 1e9 / tile))
+        cfg = q.config(w, h, b, dt, mode=mode)
+        src = device_synth_tiles(n, w, h, b, dt, dev)
+        slot = q.slot_bytes(cfg)
+        dst = torch.empty((n, slot), dtype=torch.uint8, device=dev)
+        sizes = torch.empty(n, dtype=torch.int64, device=dev); est = torch.empty(n, dtype=torch.int32, device=dev)
+        out = torch.empty((n, tile), dtype=torch.uint8, device=dev); dstat = torch.empty(n, dtype=torch.int32, device=dev)
+        offsets = torch.arange(n, device=dev, dtype=torch.int64) * slot
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        best_e = best_d = 1e9
+        for it in range(4):
+            ev[0].record()
+            q.encode_batch(cfg, src, n, dst=dst, sizes=sizes, status=est)
+            ev[1].record()
+            q.decode_batch(cfg, dst, offsets, sizes, n, out=out, status=dstat)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it:
+                best_e, best_d = min(best_e, ev[0].elapsed_time(ev[1])), min(best_d, ev[1].elapsed_time(ev[2]))
+        ok = torch.equal(out, src) and not est.any().item() and not dstat.any().item()
+        raw = n * tile
+        ratio = sizes.sum().item() / raw
+        print("| %dx%d | %d | %s | %s | %d | %.3f | %.2f | %.2f | %.0f | %.0f | %.0f |%s" % (
+            w, h, b, NAMES[dt], mname, n, ratio, best_e, best_d, raw / best_e / 1e6, raw / best_d / 1e6,
+            raw / (best_e + best_d) / 1e6, "" if ok else " ROUND TRIP FAILED"), flush=True)
+        del src, dst, out
+        torch.cuda.empty_cache()

@@ -30,13 +30,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {
     # name: (w, h, bands, dtype code, numpy dtype name, mode, cband, description)
     "c2": (512, 512, 3, 0, "uint8", 8, None, "4096 tiles 512x512x3 u8, QB3M_FTL lossless, encode+decode"),
+    "c2best": (512, 512, 3, 0, "uint8", 7, None, "tiles 512x512x3 u8, QB3M_BEST, encode+decode"),
     "c3base": (512, 512, 8, 2, "uint16", 4, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BASE, encode+decode"),
     "c3best": (512, 512, 8, 2, "uint16", 7, [0] * 8, "tiles 512x512x8 u16, core band 0, QB3M_BEST, encode+decode"),
     "c4i32": (512, 512, 1, 5, "int32", 8, None, "tiles 512x512x1 i32, QB3M_FTL lossless, encode+decode"),
     "c4u64q3": (512, 512, 1, 6, "uint64", 4, None, "tiles 512x512x1 u64, QB3M_BASE quanta 3, encode+decode"),
 }
 QUANTA = {"c4u64q3": 3}
-DEFAULT_TILES = {"c2": 4096, "c3base": 1024, "c3best": 1024, "c4i32": 2048, "c4u64q3": 1024}
+DEFAULT_TILES = {"c2": 4096, "c2best": 1024, "c3base": 1024, "c3best": 1024, "c4i32": 2048, "c4u64q3": 1024}
 # bytes moved to and from DRAM per launch (ncu), keyed by (workload, tiles per GPU, kernels); see profiles/
 NCU_TRAFFIC = {
     ("c2", 4096, "encode_kernel"): 4.929e9,

@@ -227,6 +227,7 @@ int qb3::decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const
     a.ref_compat = ref_compat != 0;
     a.ntiles = (uint32_t)ntiles;
     a.row_chunks = row_chunks;
+    a.rle_hint = rle_requested(cfg->mode);
     a.shared_sm = rows_ready != nullptr; /* the host pipeline: several batches and an encode in flight beside this one */
     a.rows_ready = rows_ready;
     a.rows_ctx = rows_ctx;

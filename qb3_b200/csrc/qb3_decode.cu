@@ -1939,13 +1939,105 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     return err != cudaSuccess ? err : ferr;
 }
 
+/*
+ * RLE streams (modes 2, 3, 6, 7) ahead of the two pass decode: a warp per stream expands the payload (deRLE0,
+ * QB3decode.cpp:267-291) into a slot of scratch memory behind a copy of the headers whose mode byte names the plain
+ * mode, and the decode then runs on (offs2, lens2), which point there. The two pass kernels never see an RLE stream;
+ * without this they leave it to parse_kernel, one lane per stream for the whole decode, twenty times slower. A stream
+ * that does not fit its slot, or is not RLE, keeps its place and its path (and its error reporting).
+ */
+__global__ void __launch_bounds__(128) derle_kernel(const DecArgs a, uint8_t *xbuf, uint64_t xslot, unsigned long long *offs2,
+                                                    unsigned long long *lens2)
+{
+    __shared__ uint8_t cbs[4 * MAXBANDS];
+    const uint32_t FULL = 0xffffffffu, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tile = blockIdx.x * 4 + warp;
+    if (tile >= a.ntiles) return;
+    const uint64_t off = a.offsets[tile], len = a.lens[tile];
+    const uint8_t *stream = a.streams + off;
+    StreamInfo info;
+    parse_header(stream, len, a, info, cbs + warp * MAXBANDS, 1); /* every lane the same: the warp stays together */
+    unsigned long long noff = off, nlen = len;
+    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
+    if (!info.bad && rle && info.data_off < 2048) {
+        const uint32_t hdr = info.data_off;
+        uint8_t *slot = xbuf + (uint64_t)tile * xslot;
+        uint8_t *out = slot + 2048, *head = out - hdr; /* payload 16 byte aligned, headers right in front of it */
+        const uint64_t cap = xslot - 2048 - 8;
+        const uint8_t *p = stream + hdr;
+        const uint64_t plen = len - hdr;
+        /* A marker is FF FF n with all three bytes inside the payload, found scanning left to right; everything else
+           is literal. The warp looks at 32 bytes at a time, copies the literals in front of the first marker together
+           and resolves that marker, so the serial rule holds and the rare markers cost one step each. */
+        uint64_t i = 0, o = 0;
+        bool fits = true;
+        while (i < plen && fits) {
+            const uint64_t pos = i + lane;
+            const uint32_t b = pos < plen ? p[pos] : 0u;
+            uint32_t nx = __shfl_down_sync(FULL, b, 1);
+            if (lane == 31) nx = pos + 1 < plen ? p[pos + 1] : 0u;
+            const bool cand = b == 0xff && nx == 0xff && pos + 2 < plen;
+            const uint32_t mask = __ballot_sync(FULL, cand);
+            const uint32_t k = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
+            const uint32_t nlit = (uint32_t)min((uint64_t)k, plen - i);
+            fits = o + 32 + 260 <= cap;
+            if (!fits) break;
+            if (lane < nlit) out[o + lane] = (uint8_t)b;
+            o += nlit;
+            i += nlit;
+            if (k == 32) continue;
+            const uint32_t c = p[i + 2];
+            if (c == 0xff) {
+                if (lane < 2) out[o + lane] = 0xff;
+                o += 2;
+            }
+            else {
+                for (uint32_t j = lane; j < 4 + c; j += 32) out[o + j] = 0;
+                o += 4 + c;
+            }
+            i += 3;
+        }
+        if (fits) {
+            for (uint32_t j = lane; j < 8; j += 32) out[o + j] = 0; /* the readers look a word past the end */
+            for (uint32_t j = lane; j < hdr; j += 32) head[j] = j == 10 ? (uint8_t)(info.mode - 2) : stream[j];
+            noff = (unsigned long long)(head - a.streams); /* may wrap: added back to a.streams modulo 2^64 */
+            nlen = hdr + o;
+        }
+    }
+    if (lane == 0) {
+        offs2[tile] = noff;
+        lens2[tile] = nlen;
+    }
+}
+
 /* kernels launched, for the bookkeeping of qb3cu_kernel_launches */
-template <typename T> static cudaError_t launch_decode_t(const DecArgs &a, cudaStream_t st, uint32_t &launches)
+template <typename T> static cudaError_t launch_decode_t(const DecArgs &a0, cudaStream_t st, uint32_t &launches)
 {
     typedef typename traits<T>::W W;
     cudaError_t err;
     bool walked = false;
     launches = 0;
+    DecArgs a = a0;
+    uint8_t *xscratch = nullptr;
+    if (a.rle_hint && a.w >= 4 && a.h >= 4) {
+        /* room for every stream expanded: what qb3_max_encoded_size allows, the headers, alignment */
+        const uint64_t xslot = ((1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) * 8 + 2) / 8 + 2048 + 64) + 15) & ~15ull;
+        const size_t idx_bytes = ((size_t)a.ntiles * 16 + 15) & ~(size_t)15;
+        cudaMemPool_t pool = scratch_pool();
+        err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&xscratch), idx_bytes + xslot * a.ntiles, pool, st)
+                   : cudaMallocAsync(reinterpret_cast<void **>(&xscratch), idx_bytes + xslot * a.ntiles, st);
+        if (err != cudaSuccess) return err;
+        unsigned long long *offs2 = reinterpret_cast<unsigned long long *>(xscratch), *lens2 = offs2 + a.ntiles;
+        derle_kernel<<<(a.ntiles + 3) / 4, 128, 0, st>>>(a, xscratch + idx_bytes, xslot, offs2, lens2);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) { cudaFreeAsync(xscratch, st); return err; }
+        a.offsets = offs2;
+        a.lens = lens2;
+        launches += 1;
+    }
+    struct FreeLater { /* the expanded streams live until the last kernel of this call has run */
+        uint8_t *p; cudaStream_t st;
+        ~FreeLater() { if (p) cudaFreeAsync(p, st); }
+    } free_later = {xscratch, st};
     if (a.w >= 4 && a.h >= 4) {
         /* two passes when a group's start bit fits its record (28 bits, 26 for the wide types); else the single
            kernel for 8 / 16 bit types and the general path for the others */

@@ -60,6 +60,7 @@ struct DecArgs {
     uint32_t ref_compat;
     uint32_t ntiles;
     uint32_t row_chunks;  /* host side only: row chunks of the two pass decode, 0 = default */
+    uint32_t rle_hint;    /* host side only: the caller expects RLE streams (cfg->mode is an RLE mode): expand them first */
     uint32_t shared_sm;   /* host side only: scans share their SMs with other kernels (many batches in flight at once) */
     /* host side only: called when the kernel that completes image rows [row0, row1) of every tile has been enqueued
        on stream s, so that a caller can start moving them out while the rest of the batch is still being parsed */

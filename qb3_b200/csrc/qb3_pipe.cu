@@ -64,6 +64,7 @@ using namespace qb3;
 struct qb3cu_pipe {
     qb3cu_config cfg;      /* as given */
     qb3cu_config dev_cfg;  /* what the kernels see: the same with the line stride of the device copy */
+    int device;            /* the device the pipe was created on: every call runs there, whatever thread makes it */
     size_t chunk, depth;
     size_t tsize, line_bytes, tile_bytes, slot;
     size_t dev_pitch;      /* bytes between tiles in device staging memory */
@@ -133,6 +134,14 @@ static bool rows_stream_out(const uint8_t *stream, uint64_t len)
     return !(m == 2 || m == 3 || m == 6 || m == 7 || m == 255);
 }
 
+/* the calling thread on the pipe's device for the length of a call (the current device is per thread) */
+struct OnDevice {
+    int before = -1;
+    bool ok;
+    explicit OnDevice(int dev) { ok = cudaGetDevice(&before) == cudaSuccess && (before == dev || cudaSetDevice(dev) == cudaSuccess); if (before == dev) before = -1; }
+    ~OnDevice() { if (before >= 0) cudaSetDevice(before); }
+};
+
 static bool drain(qb3cu_pipe *p)
 {
     bool ok = true;
@@ -165,6 +174,7 @@ qb3cu_pipe *qb3cu_pipe_create(const qb3cu_config *cfg, size_t chunk_tiles, int d
     if (cfg->stride && cfg->stride < line) return nullptr;
     qb3cu_pipe *p = new (std::nothrow) qb3cu_pipe;
     if (!p) return nullptr;
+    if (note_cuda(cudaGetDevice(&p->device)) != QB3CU_OK) { delete p; return nullptr; }
     p->cfg = *cfg;
     p->dev_cfg = *cfg;
     p->tsize = PIPE_TYPESIZE[cfg->dtype];
@@ -199,6 +209,7 @@ qb3cu_pipe *qb3cu_pipe_create(const qb3cu_config *cfg, size_t chunk_tiles, int d
 void qb3cu_pipe_destroy(qb3cu_pipe *p)
 {
     if (!p) return;
+    OnDevice here(p->device);
     for (Stage &s : p->stages) {
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
         if (s.out) { cudaStreamSynchronize(s.out); cudaStreamDestroy(s.out); }
@@ -215,6 +226,8 @@ int qb3cu_pipe_encode(qb3cu_pipe *p, const void *h_src, size_t src_tile_pitch, v
                       uint64_t *h_offsets, uint64_t *h_sizes, uint64_t *h_total, size_t ntiles)
 {
     if (!p || !h_src || !h_packed || !h_offsets || !h_sizes || !h_total) return QB3CU_ERR_PARAM;
+    OnDevice here(p->device);
+    if (!here.ok) return QB3CU_ERR_CUDA;
     if (src_tile_pitch < (p->strided ? p->dev_pitch - ((size_t)p->cfg.stride * p->tsize - p->line_bytes) : p->tile_bytes))
         return QB3CU_ERR_PARAM;
     *h_total = 0;
@@ -273,6 +286,8 @@ int qb3cu_pipe_decode(qb3cu_pipe *p, const void *h_streams, const uint64_t *h_of
                       size_t dst_tile_pitch, uint32_t *h_status, int ref_compat, size_t ntiles)
 {
     if (!p || !h_streams || !h_offsets || !h_lens || !h_dst || !h_status) return QB3CU_ERR_PARAM;
+    OnDevice here(p->device);
+    if (!here.ok) return QB3CU_ERR_CUDA;
     if (dst_tile_pitch < (p->strided ? p->dev_pitch - ((size_t)p->cfg.stride * p->tsize - p->line_bytes) : p->tile_bytes))
         return QB3CU_ERR_PARAM;
     const size_t nchunks = (ntiles + p->chunk - 1) / p->chunk;

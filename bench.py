@@ -40,8 +40,9 @@ QUANTA = {"c4u64q3": 3}
 DEFAULT_TILES = {"c2": 4096, "c2best": 1024, "c3base": 1024, "c3best": 1024, "c4i32": 2048, "c4u64q3": 1024}
 # bytes moved to and from DRAM per launch (ncu), keyed by (workload, tiles per GPU, kernels); see profiles/
 NCU_TRAFFIC = {
-    ("c2", 4096, "encode_kernel"): 4.929e9,
-    ("c2", 4096, "scan_kernel+rebuild_kernel"): 2.521e9 + 5.713e9,
+    ("c2", 4096, "encode_kernel"): 3.222e9 + 1.709e9,
+    # one of the 16 row chunks captured (scan 110.0 + 25.6 MB, rebuild 159.6 + 150.7 MB), times 16
+    ("c2", 4096, "scan_kernel+rebuild_kernel"): 16 * (135.6e6 + 310.2e6),
 }
 
 

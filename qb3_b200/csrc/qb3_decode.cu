@@ -1908,9 +1908,12 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     ScanPlan plan;
     plan.warp_smem = (uint32_t)smem1; plan.inner = 1; plan.flags = nullptr;
     for (uint32_t i = 0; i < nchunks && err == cudaSuccess; i++) {
+        /* The rebuild of the last chunk is all that is left to do when the scans are through, so that chunk is short
+           (four block rows at least, a 48th of the image at most); the others share the rest evenly. */
         RowChunk ch;
-        ch.by0 = (uint32_t)((uint64_t)nby * i / nchunks);
-        ch.by1 = (uint32_t)((uint64_t)nby * (i + 1) / nchunks);
+        const uint32_t tail = nchunks > 1 ? (nby / 48 > 4 ? nby / 48 : 4) : 0, body = nby - tail;
+        ch.by0 = i + 1 == nchunks && nchunks > 1 ? body : (uint32_t)((uint64_t)body * i / (nchunks - (nchunks > 1)));
+        ch.by1 = i + 1 == nchunks ? nby : (uint32_t)((uint64_t)body * (i + 1) / (nchunks - 1));
         ch.first = i == 0;
         ch.last = i + 1 == nchunks;
         if constexpr (NARROW)

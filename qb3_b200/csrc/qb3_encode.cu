@@ -353,6 +353,17 @@ template <typename W> struct IndexTable {
     }
 };
 
+/* mags of a difference held in the low BITS bits of d, whatever is above them (reference: QB3common.h:127-131). For
+   8 and 16 bit data in 32 bit registers: sign extend, then (s << 1) ^ (s >> 31) needs no mask afterwards. */
+template <int BITS, typename W> __device__ __forceinline__ W mags_of_delta(W d)
+{
+    if (BITS <= 16 && sizeof(W) == 4) {
+        const int32_t s = BITS == 8 ? (int32_t)(int8_t)(uint32_t)d : (int32_t)(int16_t)(uint32_t)d;
+        return (W)(uint32_t)((s << 1) ^ (s >> 31));
+    }
+    return mags<BITS, W>(d);
+}
+
 /* nibble i of the scan curve; a compile time constant for the two curves the encoder itself uses */
 template <int CURVE> __device__ __forceinline__ uint32_t curve_pos(uint64_t order, int i)
 {
@@ -491,15 +502,15 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
                     const uint32_t n15 = curve_pos<CURVE>(a.order, 15);
                     const int back = (int)((4 * (bx - 1) + (n15 & 3)) - x0) * (int)a.bands;
                     const T *q15 = own[n15 >> 2] + back;
-                    prv = ((W)q15[0] - ((W)q15[core_d] & dmask)) & TM;
+                    prv = (W)q15[0] - ((W)q15[core_d] & dmask); /* only the low BITS bits matter from here on */
                 }
                 else prv = (W)carry_prev[par * a.bands + c] & TM;
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const uint32_t n = curve_pos<CURVE>(a.order, i);
                     const T *q = own[n >> 2] + coloff[n & 3];
-                    const W v = ((W)q[0] - ((W)q[core_d] & dmask)) & TM;
-                    m[i] = mags<BITS, W>(v - prv);
+                    const W v = (W)q[0] - ((W)q[core_d] & dmask);
+                    m[i] = mags_of_delta<BITS, W>(v - prv);
                     prv = v;
                     bitsused |= m[i];
                 }
@@ -755,7 +766,7 @@ __global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ Enc
     if (a.state) {
         unsigned long long *st = a.state + (uint64_t)tile * 3 * a.bands;
         for (uint32_t c = tid; c < a.bands; c += NT) {
-            st[c] = carry_prev[(it & 1) * a.bands + c];
+            st[c] = carry_prev[(it & 1) * a.bands + c] & lowmask64(BITS);
             st[a.bands + c] = carry_rung[(it & 1) * a.bands + c];
             if (BEST) st[2 * a.bands + c] = carry_pcf[(it & 1) * a.bands + c];
         }

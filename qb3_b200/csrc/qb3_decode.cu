@@ -1825,8 +1825,10 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     constexpr bool NARROW = sizeof(T) <= 2;
     typedef typename traits<T>::W W;
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
-    uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : a.row_chunks ? a.row_chunks : 16;
-    if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* at least four block rows per chunk */
+    uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : a.row_chunks ? a.row_chunks
+                                                                                    : a.rows_ready ? 16 : 12;
+    if (nchunks > 64) nchunks = 64;
+    if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* four block rows per chunk on average, at least */
     /*
      * The scans run chunk after chunk on a stream of our own with the highest priority, the rebuilds on the caller's
      * stream, each behind the scan of its chunk. When the batch leaves most SMs unused by the scan, its CTAs (four warps,
@@ -1907,13 +1909,27 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     if (err == cudaSuccess && nchunks > 1) err = order_after(aux, st); /* the streams and the scratch memory are ready */
     ScanPlan plan;
     plan.warp_smem = (uint32_t)smem1; plan.inner = 1; plan.flags = nullptr;
+    /* Chunk sizes shrink geometrically: the rebuild of a chunk takes about 0.8 of its scan's time and cannot start
+       before that scan is over, so with each chunk 0.8 of the one before, every rebuild ends as the next scan does and
+       what is left after the last scan is the rebuild of a sliver (equal chunks leave a sixteenth of the rebuild). */
+    uint32_t bounds[65];
+    {
+        double w[64], sum = 0, acc = 0;
+        const double ratio = a.rows_ready ? 1.0 : 0.8; /* a caller that moves rows out as they complete wants them evenly */
+        for (uint32_t i = 0; i < nchunks; i++) sum += w[i] = i ? w[i - 1] * ratio : 1.0;
+        bounds[0] = 0;
+        for (uint32_t i = 0; i < nchunks; i++) {
+            acc += w[i];
+            uint32_t b = (uint32_t)(nby * acc / sum + 0.5);
+            const uint32_t lo = bounds[i] + 1, hi = nby - (nchunks - 1 - i); /* a block row at least for every chunk */
+            bounds[i + 1] = b < lo ? lo : b > hi ? hi : b;
+        }
+        bounds[nchunks] = nby;
+    }
     for (uint32_t i = 0; i < nchunks && err == cudaSuccess; i++) {
-        /* The rebuild of the last chunk is all that is left to do when the scans are through, so that chunk is short
-           (four block rows at least, a 48th of the image at most); the others share the rest evenly. */
         RowChunk ch;
-        const uint32_t tail = nchunks > 1 ? (nby / 48 > 4 ? nby / 48 : 4) : 0, body = nby - tail;
-        ch.by0 = i + 1 == nchunks && nchunks > 1 ? body : (uint32_t)((uint64_t)body * i / (nchunks - (nchunks > 1)));
-        ch.by1 = i + 1 == nchunks ? nby : (uint32_t)((uint64_t)body * (i + 1) / (nchunks - 1));
+        ch.by0 = bounds[i];
+        ch.by1 = bounds[i + 1];
         ch.first = i == 0;
         ch.last = i + 1 == nchunks;
         if constexpr (NARROW)

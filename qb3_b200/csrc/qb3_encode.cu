@@ -20,6 +20,8 @@
  * Input is read once, output written once. Headers, the stored fallback, the small-image reorder and
  * quantisation (QB3encode.cpp:151-268, 351-389, 461-485) run on the device too.
  */
+#include <cstdlib>
+
 #include "qb3_device.cuh"
 
 namespace qb3 {
@@ -384,8 +386,10 @@ __device__ __forceinline__ uint32_t packed_code32(uint32_t v, uint32_t r)
 __device__ __forceinline__ uint32_t lut_base(uint32_t r) { return (2u << r) - 4; }
 constexpr uint32_t LUT_ENTRIES = 508;
 
-template <typename T, bool BEST, int CURVE>
-__global__ void __launch_bounds__(512) encode_kernel(const __grid_constant__ EncArgs a)
+/* DENSE: built for CTAs of at most 384 threads, three to an SM (56 registers): the kernel is bound by instruction issue
+   and a third CTA gives the schedulers more warps to pick from. Used for 8 bit FTL / BASE on the Hilbert curve. */
+template <typename T, bool BEST, int CURVE, bool DENSE = false>
+__global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) encode_kernel(const __grid_constant__ EncArgs a)
 {
     typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -979,6 +983,9 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
     const int curve = a.order == HILBERT ? 1 : a.order == ZCURVE ? 2 : 0;
     auto kern = best ? (curve == 1 ? encode_kernel<T, true, 1> : curve == 2 ? encode_kernel<T, true, 2> : encode_kernel<T, true, 0>)
                      : (curve == 1 ? encode_kernel<T, false, 1> : curve == 2 ? encode_kernel<T, false, 2> : encode_kernel<T, false, 0>);
+    if constexpr (sizeof(T) == 1) {
+        if (!best && curve == 1 && threads <= 384 && !getenv("QB3CU_ENC_SPARSE")) kern = encode_kernel<T, false, 1, true>;
+    }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<(unsigned)ntiles, threads, smem, st>>>(a);

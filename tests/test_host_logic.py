@@ -200,3 +200,29 @@ def test_no_cpu_fallback():
     out = np.zeros(64, np.uint8)
     assert P.qb3_read_data(d, out.ctypes.data) == 0
     P.qb3_destroy_decoder(d)
+
+
+def test_pipe_needs_a_device_and_valid_arguments():
+    """The host pipeline has no CPU path either: without a device qb3cu_pipe_create returns NULL; bad arguments are
+    refused before anything touches CUDA."""
+    import qb3_b200 as q
+    L = q.lib()
+    cfg = q.config(64, 64, 3, q.U8)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        has_gpu = False
+    if not has_gpu:
+        with pytest.raises(RuntimeError):
+            q.Pipe(cfg)
+        assert not L.qb3cu_host_alloc(1 << 20)
+    assert not L.qb3cu_pipe_create(None, 0, 0)
+    bad = q.config(64, 64, 3, q.U8)
+    bad.width = 0
+    assert not L.qb3cu_pipe_create(C.byref(bad), 0, 0)
+    assert not L.qb3cu_pipe_create(C.byref(cfg), 0, -1)
+    assert L.qb3cu_pipe_encode(None, None, 0, None, 0, None, None, None, 0) == 1      # QB3CU_ERR_PARAM
+    assert L.qb3cu_pipe_decode(None, None, None, None, None, 0, None, 0, 0) == 1
+    L.qb3cu_pipe_destroy(None)
+    L.qb3cu_host_free(None)

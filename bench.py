@@ -327,110 +327,116 @@ def main():
     # one after the other are timed as well ("sequential").
     e2e = None
     if not args.no_e2e:
-        n2 = min(ntiles, args.e2e_tiles)
-        h_src = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
-        h_src.copy_(src[:n2])
-        h_out = torch.zeros((n2, tile_bytes), dtype=torch.uint8).pin_memory()
-        NB = 3  # packed stream buffers in rotation between the encoding and the decoding thread
-        h_packed = [torch.empty((n2 * slot,), dtype=torch.uint8).pin_memory() for _ in range(NB)]
-        h_off = [torch.zeros(n2, dtype=torch.int64) for _ in range(NB)]
-        h_sz = [torch.zeros(n2, dtype=torch.int64) for _ in range(NB)]
-        h_stat = torch.zeros(n2, dtype=torch.int32)
-        totals = [0] * NB
-        enc_pipe = q.Pipe(cfg, args.e2e_enc_chunk, args.e2e_enc_depth)
-        dec_pipe = q.Pipe(cfg, args.e2e_dec_chunk, args.e2e_dec_depth)
+        try:
+            n2 = min(ntiles, args.e2e_tiles)
+            h_src = torch.empty((n2, tile_bytes), dtype=torch.uint8).pin_memory()
+            h_src.copy_(src[:n2])
+            h_out = torch.zeros((n2, tile_bytes), dtype=torch.uint8).pin_memory()
+            NB = 3  # packed stream buffers in rotation between the encoding and the decoding thread
+            h_packed = [torch.empty((n2 * slot,), dtype=torch.uint8).pin_memory() for _ in range(NB)]
+            h_off = [torch.zeros(n2, dtype=torch.int64) for _ in range(NB)]
+            h_sz = [torch.zeros(n2, dtype=torch.int64) for _ in range(NB)]
+            h_stat = torch.zeros(n2, dtype=torch.int32)
+            totals = [0] * NB
+            enc_pipe = q.Pipe(cfg, args.e2e_enc_chunk, args.e2e_enc_depth)
+            dec_pipe = q.Pipe(cfg, args.e2e_dec_chunk, args.e2e_dec_depth)
 
-        def enc(k):
-            totals[k % NB] = enc_pipe.encode(h_src, n2, h_packed[k % NB], h_off[k % NB], h_sz[k % NB])
+            def enc(k):
+                totals[k % NB] = enc_pipe.encode(h_src, n2, h_packed[k % NB], h_off[k % NB], h_sz[k % NB])
 
-        def dec(k):
-            dec_pipe.decode(h_packed[k % NB], h_off[k % NB], h_sz[k % NB], n2, h_out, h_stat)
+            def dec(k):
+                dec_pipe.decode(h_packed[k % NB], h_off[k % NB], h_sz[k % NB], n2, h_out, h_stat)
 
-        def streaming(k0, reps):
-            """Batches k0 .. k0+reps-1 are encoded by one thread while another decodes batches k0-1 .. k0+reps-2, each as
-            soon as its streams are in host memory (batch k0-1 was encoded before the clock started): reps encodes and
-            reps decodes, nothing waits at a step boundary."""
-            encoded = [threading.Semaphore(0) for _ in range(reps + 1)]   # encoded[i]: batch k0-1+i is in host memory
-            decoded = [threading.Semaphore(0) for _ in range(reps + 1)]   # decoded[i]: batch k0-1+i has been read back
-            encoded[0].release()
-            errors = []
+            def streaming(k0, reps):
+                """Batches k0 .. k0+reps-1 are encoded by one thread while another decodes batches k0-1 .. k0+reps-2, each as
+                soon as its streams are in host memory (batch k0-1 was encoded before the clock started): reps encodes and
+                reps decodes, nothing waits at a step boundary."""
+                encoded = [threading.Semaphore(0) for _ in range(reps + 1)]   # encoded[i]: batch k0-1+i is in host memory
+                decoded = [threading.Semaphore(0) for _ in range(reps + 1)]   # decoded[i]: batch k0-1+i has been read back
+                encoded[0].release()
+                errors = []
 
-            def enc_loop():
-                try:
-                    for i in range(1, reps + 1):
-                        if i - NB >= 0:
-                            decoded[i - NB].acquire()      # the buffer this batch goes into has been decoded
-                        enc(k0 - 1 + i)
-                        encoded[i].release()
-                except Exception as e:  # noqa: BLE001 -- reported by the caller
-                    errors.append(e)
-                    for sem in encoded:
-                        sem.release()
+                def enc_loop():
+                    try:
+                        for i in range(1, reps + 1):
+                            if i - NB >= 0:
+                                decoded[i - NB].acquire()      # the buffer this batch goes into has been decoded
+                            enc(k0 - 1 + i)
+                            encoded[i].release()
+                    except Exception as e:  # noqa: BLE001 -- reported by the caller
+                        errors.append(e)
+                        for sem in encoded:
+                            sem.release()
 
-            def dec_loop():
-                try:
-                    for i in range(reps):
-                        encoded[i].acquire()
-                        dec(k0 - 1 + i)
-                        decoded[i].release()
-                except Exception as e:  # noqa: BLE001
-                    errors.append(e)
-                    for sem in decoded:
-                        sem.release()
+                def dec_loop():
+                    try:
+                        for i in range(reps):
+                            encoded[i].acquire()
+                            dec(k0 - 1 + i)
+                            decoded[i].release()
+                    except Exception as e:  # noqa: BLE001
+                        errors.append(e)
+                        for sem in decoded:
+                            sem.release()
 
-            ta, tb = threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)
-            ta.start(); tb.start(); ta.join(); tb.join()
-            if errors:
-                raise errors[0]
+                ta, tb = threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)
+                ta.start(); tb.start(); ta.join(); tb.join()
+                if errors:
+                    raise errors[0]
 
-        def timed(fn, reps, k0):
+            def timed(fn, reps, k0):
+                barrier()
+                t0 = time.perf_counter()
+                for k in range(k0, k0 + reps):
+                    fn(k)
+                barrier()
+                t = (time.perf_counter() - t0) / reps
+                if world > 1:
+                    tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    t = tt.item()
+                return t
+
+            launches_e0 = q.kernel_launches()
+            enc(0); dec(0); enc(1); dec(1)         # warm-up: buffers of both pipes reach their final size
+            streaming(2, 2)
+            k2 = max(3, args.steps // 2)
+            t_seq = timed(lambda k: (enc(k), dec(k)), k2, 4)
+            h_out.zero_()
+            k0 = 4 + k2
             barrier()
             t0 = time.perf_counter()
-            for k in range(k0, k0 + reps):
-                fn(k)
+            streaming(k0, 2 * k2)                  # batch k0 - 1, the last one of the sequential run, is its first input
             barrier()
-            t = (time.perf_counter() - t0) / reps
+            t_e2e = (time.perf_counter() - t0) / (2 * k2)
             if world > 1:
-                tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                t = tt.item()
-            return t
-
-        launches_e0 = q.kernel_launches()
-        enc(0); dec(0); enc(1); dec(1)         # warm-up: buffers of both pipes reach their final size
-        streaming(2, 2)
-        k2 = max(3, args.steps // 2)
-        t_seq = timed(lambda k: (enc(k), dec(k)), k2, 4)
-        h_out.zero_()
-        k0 = 4 + k2
-        barrier()
-        t0 = time.perf_counter()
-        streaming(k0, 2 * k2)                  # batch k0 - 1, the last one of the sequential run, is its first input
-        barrier()
-        t_e2e = (time.perf_counter() - t0) / (2 * k2)
-        if world > 1:
-            tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_e2e = tt.item()
-        assert wl in QUANTA or torch.equal(h_out, h_src), "end to end round trip differs"
-        assert not h_stat.any().item(), "tile status reports an error"
-        index_bytes = 2 * 8 * n2
-        h2d_b = n2 * tile_bytes + totals[0] + index_bytes
-        d2h_b = totals[0] + index_bytes + n2 * tile_bytes + 4 * n2
-        e2e = {"value": n2 * tile_bytes * world / t_e2e / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
-               "tiles_per_step": n2, "ms_per_step": 1e3 * t_e2e,
-               "sequential": {"value": n2 * tile_bytes * world / t_seq / 1e9, "ms_per_step": 1e3 * t_seq},
-               "note": "qb3cu_pipe_encode + qb3cu_pipe_decode on pinned host buffers: one host thread encodes batch after "
-                       "batch, a second one decodes each batch's streams from host memory as soon as they are there; a "
-                       "step = one batch encoded and one decoded; 'sequential' is the two calls one after the other on "
-                       "one thread",
-               "pipes": {"encode": [args.e2e_enc_chunk, args.e2e_enc_depth], "decode": [args.e2e_dec_chunk, args.e2e_dec_depth]}}
-        enc_pipe.close(); dec_pipe.close()
-        del h_src, h_out, h_packed
-        # restore the device state for anything that follows
-        step()
-        barrier()
+                t_e2e = tt.item()
+            assert wl in QUANTA or torch.equal(h_out, h_src), "end to end round trip differs"
+            assert not h_stat.any().item(), "tile status reports an error"
+            index_bytes = 2 * 8 * n2
+            h2d_b = n2 * tile_bytes + totals[0] + index_bytes
+            d2h_b = totals[0] + index_bytes + n2 * tile_bytes + 4 * n2
+            e2e = {"value": n2 * tile_bytes * world / t_e2e / 1e9, "unit": "GB/s",
+                   "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+                   "tiles_per_step": n2, "ms_per_step": 1e3 * t_e2e,
+                   "sequential": {"value": n2 * tile_bytes * world / t_seq / 1e9, "ms_per_step": 1e3 * t_seq},
+                   "note": "qb3cu_pipe_encode + qb3cu_pipe_decode on pinned host buffers: one host thread encodes batch after "
+                           "batch, a second one decodes each batch's streams from host memory as soon as they are there; a "
+                           "step = one batch encoded and one decoded; 'sequential' is the two calls one after the other on "
+                           "one thread",
+                   "pipes": {"encode": [args.e2e_enc_chunk, args.e2e_enc_depth], "decode": [args.e2e_dec_chunk, args.e2e_dec_depth]}}
+            enc_pipe.close(); dec_pipe.close()
+            del h_src, h_out, h_packed
+            # restore the device state for anything that follows
+            step()
+            barrier()
+        except AssertionError:  # a wrong result is never downgraded to a note
+            raise
+        except Exception as exc:  # noqa: BLE001 -- the kernel-only numbers above stand on their own; say what went wrong
+            e2e = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            barrier()
 
     if rank == 0:
         peak, peak_src = measured_peak()

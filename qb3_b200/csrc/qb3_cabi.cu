@@ -185,8 +185,36 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     smem += 508 * 4 + 64 * 2;
     if (smem > 200 * 1024) return QB3CU_ERR_PARAM;
 
-    cudaError_t err = launch_encode(a, tsize, ntiles, threads, smem, static_cast<cudaStream_t>(stream));
-    if (err == cudaSuccess) count_launches(a.rle_mode ? 2 : 1);
+    /* Few large tiles: one CTA per tile would leave most of the GPU idle (a 4096 x 4096 tile alone takes 1.5 ms), so a
+       tile is cut into parts of whole block rows, a CTA each, and the parts' bits are joined afterwards. Not for BEST
+       (its last written factor has no bound on how far back it reaches). */
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t *tmp = nullptr;
+    const bool best = a.mode == M_CF_Z || a.mode == M_CF_H;
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (!best && a.small == 0 && a.nby >= 16 && ntiles < (size_t)2 * nsm && !getenv("QB3CU_ENC_ONE_CTA")) {
+        uint32_t parts = (uint32_t)(((size_t)2 * nsm + ntiles - 1) / ntiles);
+        if (parts > a.nby / 8) parts = a.nby / 8; /* eight block rows to a part at least */
+        if (parts > 64) parts = 64;
+        if (parts >= 2) {
+            a.part_rows = (a.nby + parts - 1) / parts;
+            a.parts = (a.nby + a.part_rows - 1) / a.part_rows;
+            const uint64_t groups = (uint64_t)a.part_rows * a.nbx * a.bands;
+            a.tmp_slot = ((a.hdr_len + groups * max_group_bits(bits) / 8 + 64) + 15) & ~15ull;
+            const size_t lens_bytes = (ntiles * a.parts * 8 + 15) & ~(size_t)15;
+            if (note_cuda(cudaMallocAsync(reinterpret_cast<void **>(&tmp), lens_bytes + a.tmp_slot * a.parts * ntiles, st)) != QB3CU_OK)
+                return QB3CU_ERR_CUDA;
+            a.part_bits = reinterpret_cast<unsigned long long *>(tmp);
+            a.tmp = tmp + lens_bytes;
+        }
+    }
+    cudaError_t err = launch_encode(a, tsize, ntiles, threads, smem, st);
+    if (tmp) {
+        const cudaError_t ferr = cudaFreeAsync(tmp, st);
+        if (err == cudaSuccess) err = ferr;
+    }
+    if (err == cudaSuccess) count_launches((a.rle_mode ? 2 : 1) + (a.parts > 1 ? 1 : 0));
     return note_cuda(err);
 }
 

@@ -44,6 +44,12 @@ struct EncArgs {
     uint32_t best_off;    /* byte offset of the BEST mode scratch in shared memory, 8 byte aligned */
     uint32_t lut_off;     /* byte offset of the code tables in shared memory, 8 byte aligned */
     uint32_t hdr_len, hdr_stored_len;
+    /* a tile coded by several CTAs (few, large tiles): each takes part_rows block rows and writes its bits, from bit 0,
+       into its own region of tmp; stitch_kernel then joins the parts in the tile's slot */
+    uint32_t parts, part_rows;
+    uint64_t tmp_slot;          /* bytes per part region, multiple of 16 */
+    uint8_t *tmp;
+    unsigned long long *part_bits; /* [tile][part] bits written, all ones when the part did not fit */
     uint8_t hdr[MAXHDR];        /* headers up to and including "DT", mode byte = mode */
     uint8_t hdr_stored[MAXHDR]; /* same for the stored fallback (mode 255, no CB / SC) */
     uint8_t cband[MAXBANDS];

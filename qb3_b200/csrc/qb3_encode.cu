@@ -414,9 +414,13 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem + a.lut_off);                                     /* [508] */
     uint16_t *cs_lut = reinterpret_cast<uint16_t *>(lut + LUT_ENTRIES);                                 /* [2^U] */
 
-    const uint32_t tid = threadIdx.x, NT = blockDim.x, tile = blockIdx.x;
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t multi = a.parts > 1, tile = multi ? blockIdx.x / a.parts : blockIdx.x, part = multi ? blockIdx.x % a.parts : 0;
+    const uint32_t by_lo = part * a.part_rows, by_hi = multi ? min(a.nby, by_lo + a.part_rows) : a.nby;
     const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
-    uint8_t *dst = a.dst + (uint64_t)tile * a.slot;
+    uint8_t *dst = multi ? a.tmp + ((uint64_t)tile * a.parts + part) * a.tmp_slot : a.dst + (uint64_t)tile * a.slot;
+    const uint64_t room = multi ? a.tmp_slot : a.slot;
+    const uint32_t hdr_len = part == 0 ? a.hdr_len : 0;
     const bool use_step = a.mode != M_FTL;
 
     /* running state in, zero unless the caller keeps it across calls (reference: QB3encode.h:391-394) */
@@ -435,9 +439,42 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
         for (uint32_t i = tid; i < (1u << U); i += NT) cs_lut[i] = (uint16_t)cs_entry(U, i);
     }
     __syncthreads();
-    for (uint32_t i = tid; i < a.hdr_len; i += NT) reinterpret_cast<uint8_t *>(win)[i] = a.hdr[i];
+    for (uint32_t i = tid; i < hdr_len; i += NT) reinterpret_cast<uint8_t *>(win)[i] = a.hdr[i];
+    if (part > 0 && tid < a.bands) {
+        /* A later part starts from the state the blocks before it leave behind, and both pieces of it are neighbour
+           look-ups: the last value and the rung of the last block of the block row above (for its rung, the last value
+           of the block before that one). Straight from global memory: 17 pixels per band. */
+        const T *img = reinterpret_cast<const T *>(src);
+        const W TMp = (W)lowmask64(BITS);
+        const uint32_t cc = tid, cb = a.cband[cc];
+        auto pixel = [&](uint32_t x, uint32_t y, uint32_t k) -> W {
+            uint64_t v = img[(uint64_t)y * a.stride + (uint64_t)x * a.bands + k];
+            if (a.quanta > 1) v = quantize_value<BITS>(v, a.quanta, a.away != 0, a.is_signed != 0);
+            return (W)v;
+        };
+        auto value = [&](uint32_t x, uint32_t y) -> W {
+            W v = pixel(x, y, cc);
+            if (cb != cc) v -= pixel(x, y, cb);
+            return v & TMp;
+        };
+        const uint32_t n15 = curve_pos<CURVE>(a.order, 15);
+        const uint32_t by = by_lo - 1, bx = a.nbx - 1, x0 = min(4 * bx, a.vw - 4), y0 = 4 * by; /* not the last block row */
+        W before = (W)carry_prev[cc] & TMp; /* last value of the block ahead of that one; the caller's state at the very start */
+        if (bx > 0) before = value(min(4 * (bx - 1), a.vw - 4) + (n15 & 3), y0 + (n15 >> 2));
+        else if (by > 0) before = value(x0 + (n15 & 3), 4 * (by - 1) + (n15 >> 2));
+        W used = 0, last = before;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t n = curve_pos<CURVE>(a.order, i);
+            const W v = value(x0 + (n & 3), y0 + (n >> 2));
+            used |= mags<BITS, W>((v - last) & TMp);
+            last = v;
+        }
+        carry_prev[cc] = (unsigned long long)last;
+        carry_rung[cc] = (uint8_t)topbit((W)(used | 1));
+    }
 
-    uint32_t wbits = a.hdr_len * 8;    /* bits waiting in the window */
+    uint32_t wbits = hdr_len * 8;      /* bits waiting in the window */
     uint64_t flushed = 0;              /* 16 byte units already in global memory */
     bool overflow = false;             /* output would not fit the slot: the tile ends up stored */
     uint32_t it = 0;
@@ -450,11 +487,11 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
         const uint32_t xs = min(4 * bx0, a.vw - 4), xe = min(4 * (bx0 + nblk), a.vw);
         stage_rows<T>(a, src, stage + buf * stage_bytes, min(4 * by, a.vh - 4), xs, xe - xs);
     };
-    if (a.small != 3) issue(0, 0, 0);
+    if (a.small != 3) issue(by_lo, 0, 0);
     cp_async_commit();
 
     /* a.small == 3: sixteen pixels or fewer are stored outright (reference: QB3encode.cpp:490-491) */
-    for (uint32_t by = 0; by < a.nby && a.small != 3; by++) {
+    for (uint32_t by = by_lo; by < by_hi && a.small != 3; by++) {
         const uint32_t y0 = min(4 * by, a.vh - 4);
         for (uint32_t sg = 0; sg < a.segs; sg++, it++) {
             const uint32_t bx0 = sg * a.seg_blocks, nblk = min(a.seg_blocks, a.nbx - bx0), ng = nblk * a.bands;
@@ -462,7 +499,7 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
             const uint32_t par = it & 1;
             {   /* next segment's rows start travelling now; this segment's have had a whole iteration to land */
                 const uint32_t nsg = sg + 1 < a.segs ? sg + 1 : 0, nby = nsg ? by : by + 1;
-                if (nby < a.nby) issue(nby, nsg, par ^ 1);
+                if (nby < by_hi) issue(nby, nsg, par ^ 1);
                 cp_async_commit();
                 cp_async_wait<1>();
             }
@@ -750,10 +787,10 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
             /* complete 16 byte units leave for global memory, the rest is carried */
             const uint32_t B = wbits + total, nu = B >> 7;
             for (uint32_t k = tid; k < nu; k += NT) {
-                if ((flushed + k + 1) * 16 <= a.slot)
+                if ((flushed + k + 1) * 16 <= room)
                     st_stream16(dst + (flushed + k) * 16, reinterpret_cast<const uint4 *>(win)[k]);
             }
-            if ((flushed + nu) * 16 > a.slot) overflow = true;
+            if ((flushed + nu) * 16 > room) overflow = true;
             uint32_t cw = 0;
             if (tid < 4) cw = win[nu * 4 + tid];
             __syncthreads();
@@ -766,8 +803,8 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
     }
     __syncthreads();
 
-    /* running state out (reference: QB3encode.h:446-449) */
-    if (a.state) {
+    /* running state out (reference: QB3encode.h:446-449); of a tile in parts, the last part's */
+    if (a.state && (!multi || part + 1 == a.parts)) {
         unsigned long long *st = a.state + (uint64_t)tile * 3 * a.bands;
         for (uint32_t c = tid; c < a.bands; c += NT) {
             st[c] = carry_prev[(it & 1) * a.bands + c] & lowmask64(BITS);
@@ -777,9 +814,13 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
     }
 
     uint64_t len_bytes = flushed * 16 + ((wbits + 7) >> 3);
-    if ((flushed + 1) * 16 > a.slot) overflow = true;
+    if ((flushed + 1) * 16 > room) overflow = true;
     if (wbits && !overflow && tid == 0)
         st_stream16(dst + flushed * 16, reinterpret_cast<const uint4 *>(win)[0]);
+    if (multi) { /* stitch_kernel puts the parts together and settles size, status and the stored fallback */
+        if (tid == 0) a.part_bits[(uint64_t)tile * a.parts + part] = overflow ? ~0ull : flushed * 128 + wbits;
+        return;
+    }
 
     /* stored fallback when coding did not shrink the tile (reference: QB3encode.cpp:570-573, 461-485) */
     /* with an RLE mode the choice is left to rle_kernel: the reference tries RLE first (QB3encode.cpp:536-573) */
@@ -799,6 +840,79 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) e
     }
 }
 
+
+/* ------------------------------------------------------------------ joining the parts of a tile */
+
+/*
+ * A tile coded in parts (encode_kernel with a.parts > 1): part p holds len_p bits from bit 0 of its region. The stream is
+ * their concatenation; CTA (p, tile) writes the 32 bit words of the slot whose first bit lies in part p, taking the
+ * low bits of its first word from the tail of part p - 1. Then, as at the end of encode_kernel: size, status, and
+ * the stored fallback when coding did not pay or a part did not fit (reference: QB3encode.cpp:570-573, 461-485).
+ */
+__global__ void __launch_bounds__(256) stitch_kernel(const __grid_constant__ EncArgs a, uint32_t tsize)
+{
+    const uint32_t part = blockIdx.x, tile = blockIdx.y, tid = threadIdx.x, NT = blockDim.x;
+    const unsigned long long *lens = a.part_bits + (uint64_t)tile * a.parts;
+    unsigned long long start = 0, total = 0;
+    bool overflow = false;
+    for (uint32_t q = 0; q < a.parts; q++) {
+        const unsigned long long l = lens[q];
+        overflow |= l == ~0ull;
+        if (q < part) start += l;
+        total += l;
+    }
+    uint8_t *dst = a.dst + (uint64_t)tile * a.slot;
+    const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
+    const uint64_t len_bytes = (total + 7) >> 3;
+    overflow |= ((len_bytes + 15) & ~15ull) > a.slot;
+    if (overflow || (!a.rle_mode && a.raw_size <= len_bytes)) {
+        if (part == 0)
+            for (uint32_t i = tid; i < a.hdr_stored_len; i += NT) dst[i] = a.hdr_stored[i];
+        const uint64_t line = (uint64_t)a.w * a.bands * tsize, pitch = a.stride * tsize;
+        const uint64_t per = (a.raw_size + a.parts - 1) / a.parts, lo = per * part, hi = min(a.raw_size, lo + per);
+        for (uint64_t i = lo + tid; i < hi; i += NT) {
+            const uint64_t y = i / line, x = i - y * line;
+            dst[a.hdr_stored_len + i] = src[y * pitch + x];
+        }
+        if (part == 0 && tid == 0) {
+            a.sizes[tile] = a.hdr_stored_len + a.raw_size;
+            if (a.status) a.status[tile] = 0;
+        }
+        return;
+    }
+    const unsigned long long len = lens[part], end = start + len;
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(a.tmp + ((uint64_t)tile * a.parts + part) * a.tmp_slot);
+    const uint32_t *prev = part ? reinterpret_cast<const uint32_t *>(a.tmp + ((uint64_t)tile * a.parts + part - 1) * a.tmp_slot) : nullptr;
+    const unsigned long long plen = part ? lens[part - 1] : 0;
+    uint32_t *out = reinterpret_cast<uint32_t *>(dst);
+    const uint32_t sh = (uint32_t)start & 31;           /* bits of the first word that belong to the part before */
+    const unsigned long long w0 = start >> 5;
+    /* words whose first bit is in [start, end), and the word start falls into when it begins inside it */
+    const unsigned long long wfirst = sh ? w0 + 1 : w0, wend = (end + 31) >> 5, nin = (len + 31) >> 5;
+    auto word_at = [&](long long o) -> uint32_t { /* 32 bits of this part from local bit offset o, zeros outside */
+        const long long i = o >> 5;
+        const uint32_t r = (uint32_t)o & 31;
+        const uint32_t lo = i >= 0 && (unsigned long long)i < nin ? in[i] : 0u;
+        const uint32_t hi = r && i + 1 >= 0 && (unsigned long long)(i + 1) < nin ? in[i + 1] : 0u;
+        return r ? (lo >> r) | (hi << (32 - r)) : lo;
+    };
+    if (sh && tid == 0 && len) { /* the shared word: the last sh bits of the part before, then this part's first bits */
+        const unsigned long long pb = plen - sh; /* parts are thousands of bits long */
+        const uint32_t r = (uint32_t)pb & 31;
+        const unsigned long long i = pb >> 5, pn = (plen + 31) >> 5;
+        const uint32_t lo = prev[i], hi = r && i + 1 < pn ? prev[i + 1] : 0u;
+        const uint32_t tail = (r ? (lo >> r) | (hi << (32 - r)) : lo) & ((1u << sh) - 1);
+        out[w0] = tail | (in[0] << sh);
+    }
+    /* a word that ends beyond this part belongs to the next one, unless this is the last part */
+    const unsigned long long wstop = (part + 1 < a.parts && (end & 31)) ? end >> 5 : wend;
+    for (unsigned long long w = wfirst + tid; w < wstop; w += NT)
+        out[w] = word_at((long long)(32 * w) - (long long)start);
+    if (part == 0 && tid == 0) {
+        a.sizes[tile] = len_bytes;
+        if (a.status) a.status[tile] = 0;
+    }
+}
 
 /* ------------------------------------------------------------------ RLE0 byte pass */
 
@@ -988,8 +1102,12 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
     }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    kern<<<(unsigned)ntiles, threads, smem, st>>>(a);
+    kern<<<(unsigned)(ntiles * (a.parts > 1 ? a.parts : 1)), threads, smem, st>>>(a);
     err = cudaGetLastError();
+    if (err == cudaSuccess && a.parts > 1) {
+        stitch_kernel<<<dim3(a.parts, (unsigned)ntiles), 256, 0, st>>>(a, (uint32_t)sizeof(T));
+        err = cudaGetLastError();
+    }
     if (err != cudaSuccess || !a.rle_mode) return err;
     rle_kernel<<<(unsigned)((ntiles + 3) / 4), 128, 0, st>>>(a, (uint32_t)ntiles);
     return cudaGetLastError();

@@ -413,3 +413,72 @@ def test_cli_encode_decode_bandmix_and_folder(tmp_path):
     for t in range(3):
         assert (o / ("t%d.qb3" % t)).read_bytes() == oracle().encode(rgb[t], mode=MODE_FTL)
     assert (o / "g.qb3").read_bytes() == oracle().encode(gray16, mode=MODE_FTL)
+
+
+def test_two_pipes_on_two_threads():
+    """An encode pipe and a decode pipe used at the same time from two host threads (what bench.py's end to end leg
+    does): results identical to the calls made alone."""
+    import threading
+    torch = torch_mod()
+    n, w, h, b = 96, 128, 96, 3
+    tiles = synth_tiles(n, w, h, b, np.uint8)
+    cfg = q.config(w, h, b, q.U8, mode=MODE_FTL)
+    ep, dp = q.Pipe(cfg, 16, 3), q.Pipe(cfg, 32, 2)
+    h_src = torch.from_numpy(tiles.reshape(n, -1)).pin_memory()
+    packed = [torch.zeros(n * q.slot_bytes(cfg), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    off = [torch.zeros(n, dtype=torch.int64) for _ in range(2)]
+    sz = [torch.zeros(n, dtype=torch.int64) for _ in range(2)]
+    out = torch.zeros_like(h_src).pin_memory()
+    st = torch.ones(n, dtype=torch.int32)
+    ep.encode(h_src, n, packed[0], off[0], sz[0])
+    errors = []
+
+    def run(f, *a):
+        try:
+            f(*a)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    for k in range(1, 5):   # encode into one buffer while the other one is decoded
+        ta = threading.Thread(target=run, args=(ep.encode, h_src, n, packed[k % 2], off[k % 2], sz[k % 2]))
+        tb = threading.Thread(target=run, args=(dp.decode, packed[(k - 1) % 2], off[(k - 1) % 2], sz[(k - 1) % 2], n, out, st))
+        out.zero_(); st.fill_(1)
+        ta.start(); tb.start(); ta.join(); tb.join()
+        assert not errors, errors
+        assert not st.any().item() and torch.equal(out, h_src)
+    for t in (0, n // 2, n - 1):
+        o, s = int(off[0][t]), int(sz[0][t])
+        assert packed[0][o:o + s].numpy().tobytes() == oracle().encode(tiles[t], mode=MODE_FTL)
+    ep.close(); dp.close()
+
+
+@pytest.mark.parametrize("shape,dt,kw", [
+    ((1, 1024, 1024, 3), np.uint8, dict(mode=MODE_FTL)),          # one large tile: 32 parts
+    ((2, 517, 1030, 1), np.uint16, dict(mode=MODE_BASE)),         # ragged size, last block row shifted up
+    ((3, 300, 260, 4), np.int16, dict(mode=MODE_BASE, quanta=3)), # quantised, derived bands
+    ((1, 8, 2048, 2), np.uint8, dict(mode=MODE_BASE, cband=[1, 1])),  # two blocks to a row: the neighbour look-ups wrap rows
+    ((1, 4, 512, 1), np.int32, dict(mode=MODE_FTL)),              # one block to a row
+    ((2, 640, 400, 3), np.uint8, dict(mode=6)),                   # BASE + RLE over stitched parts
+])
+def test_batch_large_tiles_in_parts_match_oracle(shape, dt, kw):
+    """Few large tiles are coded by several CTAs each and stitched (encode_kernel parts + stitch_kernel): byte identical
+    to the oracle, and decodable."""
+    torch = torch_mod()
+    n, w, h, b = shape
+    tiles = synth_tiles(n, w, h, b, dt)
+    cfg, dst, sizes, status = encode_tiles(tiles, **kw)
+    sz, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
+    for t in range(n):
+        want = oracle().encode(tiles[t], **kw)
+        assert int(sz[t]) == len(want) and dst_h[t, :sz[t]].tobytes() == want, "tile %d differs from the oracle" % t
+    offsets = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, n)
+    torch.cuda.synchronize()
+    assert not st.cpu().numpy().any()
+    if kw.get("quanta", 1) == 1:
+        assert np.array_equal(out.cpu().numpy().view(dt).reshape(tiles.shape), tiles)
+    # incompressible content: the parts do not pay, the tile is stored
+    noise = np.random.default_rng(3).integers(0, 256, (1, 256, 512, 3), dtype=np.uint8)
+    cfg2, dst2, sizes2, _ = encode_tiles(noise, mode=MODE_BASE)
+    want = oracle().encode(noise[0], mode=MODE_BASE)
+    assert dst2.cpu().numpy()[0, :int(sizes2[0])].tobytes() == want and want[10] == 255

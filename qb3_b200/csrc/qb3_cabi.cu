@@ -11,6 +11,7 @@
 namespace qb3 {
 cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st);
 cudaError_t launch_decode(const DecArgs &a, uint32_t tsize, cudaStream_t st, uint32_t &launches);
+cudaMemPool_t scratch_pool(); /* qb3_decode.cu: the library's own stream ordered pool, which keeps its memory */
 cudaError_t launch_pack(const uint8_t *slots, uint64_t slot, const unsigned long long *sizes, uint8_t *packed,
                         unsigned long long *offsets, unsigned long long *total, uint32_t ntiles, cudaStream_t st);
 
@@ -193,8 +194,8 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     const bool best = a.mode == M_CF_Z || a.mode == M_CF_H;
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (!best && a.small == 0 && a.nby >= 16 && ntiles < (size_t)2 * nsm && !getenv("QB3CU_ENC_ONE_CTA")) {
-        uint32_t parts = (uint32_t)(((size_t)2 * nsm + ntiles - 1) / ntiles);
+    if (!best && a.small == 0 && a.nby >= 16 && ntiles < (size_t)4 * nsm && !getenv("QB3CU_ENC_ONE_CTA")) {
+        uint32_t parts = (uint32_t)(((size_t)6 * nsm + ntiles - 1) / ntiles); /* a few CTAs per SM to balance the load */
         if (parts > a.nby / 8) parts = a.nby / 8; /* eight block rows to a part at least */
         if (parts > 64) parts = 64;
         if (parts >= 2) {
@@ -203,7 +204,10 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
             const uint64_t groups = (uint64_t)a.part_rows * a.nbx * a.bands;
             a.tmp_slot = ((a.hdr_len + groups * max_group_bits(bits) / 8 + 64) + 15) & ~15ull;
             const size_t lens_bytes = (ntiles * a.parts * 8 + 15) & ~(size_t)15;
-            if (note_cuda(cudaMallocAsync(reinterpret_cast<void **>(&tmp), lens_bytes + a.tmp_slot * a.parts * ntiles, st)) != QB3CU_OK)
+            cudaMemPool_t pool = scratch_pool();
+            const size_t tmp_bytes = lens_bytes + a.tmp_slot * a.parts * ntiles;
+            if (note_cuda(pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&tmp), tmp_bytes, pool, st)
+                               : cudaMallocAsync(reinterpret_cast<void **>(&tmp), tmp_bytes, st)) != QB3CU_OK)
                 return QB3CU_ERR_CUDA;
             a.part_bits = reinterpret_cast<unsigned long long *>(tmp);
             a.tmp = tmp + lens_bytes;

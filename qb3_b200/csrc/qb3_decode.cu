@@ -1758,7 +1758,7 @@ template <typename T> static cudaError_t launch_walk_any(const DecArgs &a, cudaS
  *  - it never reuses a block freed on another stream by making the new owner wait for the old one: batches decoded
  *    concurrently on different streams must stay concurrent (they would otherwise run one after the other)
  */
-static cudaMemPool_t scratch_pool()
+cudaMemPool_t scratch_pool()
 {
     static cudaMemPool_t pools[64] = {};
     static std::mutex mu;

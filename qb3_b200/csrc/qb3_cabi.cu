@@ -198,7 +198,7 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
         uint32_t parts = (uint32_t)(((size_t)6 * nsm + ntiles - 1) / ntiles); /* a few CTAs per SM to balance the load */
         if (parts > a.nby / 8) parts = a.nby / 8; /* eight block rows to a part at least */
         if (parts > 64) parts = 64;
-        if (parts >= 2) {
+        if (parts >= 3) { /* in two parts the joining pass costs more than the second CTA brings (measured) */
             a.part_rows = (a.nby + parts - 1) / parts;
             a.parts = (a.nby + a.part_rows - 1) / a.part_rows;
             const uint64_t groups = (uint64_t)a.part_rows * a.nbx * a.bands;

@@ -389,7 +389,7 @@ constexpr uint32_t LUT_ENTRIES = 508;
 /* DENSE: built for CTAs of at most 384 threads, three to an SM (56 registers): the kernel is bound by instruction issue
    and a third CTA gives the schedulers more warps to pick from. Used for 8 bit FTL / BASE on the Hilbert curve. */
 template <typename T, bool BEST, int CURVE, bool DENSE = false>
-__global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? 3 : BEST ? 1 : 2) encode_kernel(const __grid_constant__ EncArgs a)
+__global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BEST ? 1 : 2) encode_kernel(const __grid_constant__ EncArgs a)
 {
     typedef typename traits<T>::W W;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
@@ -1099,6 +1099,9 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
                      : (curve == 1 ? encode_kernel<T, false, 1> : curve == 2 ? encode_kernel<T, false, 2> : encode_kernel<T, false, 0>);
     if constexpr (sizeof(T) == 1) {
         if (!best && curve == 1 && threads <= 384 && !getenv("QB3CU_ENC_SPARSE")) kern = encode_kernel<T, false, 1, true>;
+    }
+    if constexpr (sizeof(T) <= 2) { /* BEST: two CTAs to an SM (85 registers) hide the wait for the threads with index groups */
+        if (best && curve == 1 && threads <= 384 && !getenv("QB3CU_ENC_SPARSE")) kern = encode_kernel<T, true, 1, true>;
     }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

@@ -40,9 +40,10 @@ QUANTA = {"c4u64q3": 3}
 DEFAULT_TILES = {"c2": 4096, "c2best": 1024, "c3base": 1024, "c3best": 1024, "c4i32": 2048, "c4u64q3": 1024}
 # bytes moved to and from DRAM per launch (ncu), keyed by (workload, tiles per GPU, kernels); see profiles/
 NCU_TRAFFIC = {
-    ("c2", 4096, "encode_kernel"): 3.222e9 + 1.709e9,
-    # one of the 16 row chunks captured (scan 110.0 + 25.6 MB, rebuild 159.6 + 150.7 MB), times 16
-    ("c2", 4096, "scan_kernel+rebuild_kernel"): 16 * (135.6e6 + 310.2e6),
+    ("c2", 4096, "encode_kernel"): 3.224e9 + 1.711e9,
+    # the first of the 12 row chunks captured (scan 368.8 + 145.8 MB, rebuild 536.6 + 629.3 MB); it holds
+    # 1 / sum(0.8^i, i < 12) = 0.2148 of the block rows
+    ("c2", 4096, "scan_kernel+rebuild_kernel"): (514.6e6 + 1165.9e6) / 0.2148,
 }
 
 

@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 import qb3_b200 as q
-from helpers import (CONTENT_KINDS, DTYPES, MODE_BASE, MODE_BEST, MODE_FTL, PRODUCT_SO, QB3Lib, content, dtype_code,
-                     golden_cases, golden_check_stream, golden_image, golden_kwargs, oracle, synth_tiles)
+from helpers import (CONTENT_KINDS, DTYPES, MODE_BASE, MODE_BEST, MODE_FTL, PRODUCT_SO, REF_SO, QB3Lib, content, dtype_code,
+                     golden_cases, golden_check_stream, golden_image, golden_kwargs, have_ref, oracle, synth_tiles)
 
 pytestmark = pytest.mark.gpu
 
@@ -482,3 +482,52 @@ def test_batch_large_tiles_in_parts_match_oracle(shape, dt, kw):
     cfg2, dst2, sizes2, _ = encode_tiles(noise, mode=MODE_BASE)
     want = oracle().encode(noise[0], mode=MODE_BASE)
     assert dst2.cpu().numpy()[0, :int(sizes2[0])].tobytes() == want and want[10] == 255
+
+
+@pytest.mark.parametrize("dt,mode", [(np.uint8, MODE_BASE), (np.uint8, MODE_BEST), (np.uint16, MODE_BEST), (np.int32, MODE_BASE),
+                                     (np.uint8, MODE_FTL), (np.uint64, MODE_BEST), (np.int16, MODE_BASE), (np.int8, 1)])
+def test_damaged_streams_decode_like_the_oracle(dt, mode):
+    """One flipped payload bit per stream: wherever the oracle (and the compiled reference, when it is there) still
+    decodes, the device must produce the very same pixels; where it reports failure, so must the device. A damaged
+    stream wanders through rung switches, factors and index tables no encoder would write."""
+    torch = torch_mod()
+    n, w, h, b = 48, 64, 64, 3
+    kinds = [k for k in CONTENT_KINDS]
+    tiles = np.stack([content(kinds[t % len(kinds)], w, h, b, dt, seed=100 + t) for t in range(n)])
+    cfg = q.config(w, h, b, dtype_code(dt), mode=mode)
+    rng = np.random.default_rng(2024)
+    streams = []
+    for t in range(n):
+        s = bytearray(oracle().encode(tiles[t], mode=mode))
+        hdr = oracle().info(bytes(s))["data_offset"]
+        if s[10] != 255 and len(s) > hdr + 4:
+            pos = int(rng.integers(hdr * 8, len(s) * 8))
+            s[pos >> 3] ^= 1 << (pos & 7)
+        streams.append(bytes(s))
+    slot = max(len(s) for s in streams) + 64
+    buf = np.zeros((n, slot), np.uint8)
+    for t, s in enumerate(streams):
+        buf[t, :len(s)] = np.frombuffer(s, np.uint8)
+    d = torch.from_numpy(buf).cuda()
+    sizes = torch.tensor([len(s) for s in streams], dtype=torch.int64, device="cuda")
+    offsets = torch.arange(n, device="cuda", dtype=torch.int64) * slot
+    out, st = q.decode_batch(cfg, d, offsets, sizes, n)
+    torch.cuda.synchronize()
+    out_h, st_h = out.cpu().numpy().view(dt).reshape(tiles.shape), st.cpu().numpy()
+    ref = QB3Lib(REF_SO, 16) if have_ref() else None
+    agree = 0
+    for t in range(n):
+        want = oracle().decode(streams[t])
+        if ref is not None and want is not None:
+            # What the oracle decodes, the reference decodes (its pixels differ only by its band map default, SURVEY D1).
+            # The converse does not hold: in a damaged common factor group whose factor claims a rung of its own equal
+            # to 0 the reference reads its table at index -1 (QB3decode.h:651) and carries on with whatever is there;
+            # the oracle and the device report failure.
+            assert ref.decode(streams[t]) is not None, "tile %d: the oracle decodes what the reference rejects" % t
+        if want is None:
+            assert st_h[t] != q.TILE_OK, "tile %d: the oracle rejects the stream, the device accepts it" % t
+        else:
+            assert st_h[t] == q.TILE_OK, "tile %d: the oracle decodes the stream, the device reports %d" % (t, st_h[t])
+            assert np.array_equal(out_h[t], want), "tile %d decodes differently" % t
+            agree += 1
+    assert agree > 0

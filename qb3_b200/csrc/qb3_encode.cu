@@ -386,6 +386,51 @@ __device__ __forceinline__ uint32_t packed_code32(uint32_t v, uint32_t r)
 __device__ __forceinline__ uint32_t lut_base(uint32_t r) { return (2u << r) - 4; }
 constexpr uint32_t LUT_ENTRIES = 508;
 
+/* 8 / 16 bit data: the 16 values of a group as packed codes (len << 20) | bits, step flip first when asked for; the
+   rung 1..7 codes (middle swap included) come from the shared table, higher rungs are computed */
+__device__ __forceinline__ void group_codes(uint32_t (&m)[16], uint32_t rung, bool use_step, const uint32_t *lut)
+{
+    if (use_step) {
+        const int k = step_index<uint32_t>(m, rung);
+#pragma unroll
+        for (int i = 0; i < 16; i++) if (i == k) m[i] ^= 1u << rung;
+    }
+    if (rung < 8) {
+        const uint32_t *t = lut + lut_base(rung);
+#pragma unroll
+        for (int i = 0; i < 16; i++) m[i] = t[m[i]];
+    }
+    else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) m[i] = packed_code32(m[i], rung);
+    }
+}
+
+/* the packed codes of a group into the bit window: 8 bit data three codes to a word, 16 bit data two */
+template <int BITS> __device__ __forceinline__ void put_codes(Packer &pk, const uint32_t (&c)[16])
+{
+    if (BITS == 8) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            const uint32_t a0 = c[3 * j], l0 = a0 >> 20;
+            uint32_t cw = a0 & 0xfffffu, cl = l0;
+            if (j < 5) {
+                const uint32_t a1 = c[3 * j + 1], a2 = c[3 * j + 2], l01 = l0 + (a1 >> 20);
+                cw |= ((a1 & 0xfffffu) << l0) | ((a2 & 0xfffffu) << l01);
+                cl = l01 + (a2 >> 20);
+            }
+            pk.put32(cw, cl);
+        }
+    }
+    else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const uint32_t a0 = c[i], a1 = c[i + 1], l0 = a0 >> 20;
+            pk.put64((uint64_t)(a0 & 0xfffffu) | ((uint64_t)(a1 & 0xfffffu) << l0), l0 + (a1 >> 20));
+        }
+    }
+}
+
 /* DENSE: built for CTAs of at most 384 threads, three to an SM (56 registers): the kernel is bound by instruction issue
    and a third CTA gives the schedulers more warps to pick from. Used for 8 bit FTL / BASE on the Hilbert curve. */
 template <typename T, bool BEST, int CURVE, bool DENSE = false>
@@ -411,6 +456,7 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     /* 8 / 16 bit FTL and BASE: the rung 1..7 group codes (middle swap included) and the rung switches as shared
        tables, generated here from the closed forms; (len << 20) | bits and (len << 12) | bits */
     constexpr bool USE_LUT = !BEST && BITS <= 16;
+    constexpr bool HAVE_LUT = BITS <= 16; /* BEST codes its plain groups, the bulk, through the same tables */
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem + a.lut_off);                                     /* [508] */
     uint16_t *cs_lut = reinterpret_cast<uint16_t *>(lut + LUT_ENTRIES);                                 /* [2^U] */
 
@@ -431,7 +477,7 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
         if (BEST) carry_pcf[c] = st ? st[2 * a.bands + c] : 0ull;
     }
     for (uint32_t i = tid; i < a.win_words; i += NT) win[i] = 0;
-    if (USE_LUT) {
+    if (HAVE_LUT) {
         for (uint32_t i = tid; i < LUT_ENTRIES; i += NT) {
             const uint32_t r = topbit32(i + 4) - 1, v = i - lut_base(r);
             lut[i] = packed_code32(mswap<uint32_t>(v, r), r);
@@ -650,6 +696,15 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
                                 cfl = (cs_entry(U, (cfrung - trung) & UMASK) >> 12) + single_len<W>(cm2 ^ ((W)1 << cfrung), cfrung - 1);
                             l_diff = l_same + cfl;
                         }
+                        else if constexpr (HAVE_LUT) { /* lengths only: the values are still needed for the index candidate */
+                            uint32_t cc[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i++) cc[i] = (uint32_t)m[i];
+                            group_codes(cc, rung, true, lut);
+                            l_plain = cs >> 12;
+#pragma unroll
+                            for (int i = 0; i < 16; i++) l_plain += cc[i] >> 20;
+                        }
                         else l_plain = (cs >> 12) + body_len<W>(m, rung);
                         idx_elig = rung > 3 && rung < 63;
                         if (idx_elig) {
@@ -747,7 +802,14 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
             }
             else if (BEST && active && bitsused > 1) { /* plain group, always with step coding */
                 pk.put32(cs & 0xfff, cs >> 12);
-                ValuePut<W, BITS>::put_body(pk, m, rung);
+                if constexpr (HAVE_LUT) {
+                    uint32_t cc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) cc[i] = (uint32_t)m[i];
+                    group_codes(cc, rung, true, lut);
+                    put_codes<BITS>(pk, cc);
+                }
+                else ValuePut<W, BITS>::put_body(pk, m, rung);
             }
             else if (active) {
                 pk.put32(cs & 0xfff, cs >> 12);

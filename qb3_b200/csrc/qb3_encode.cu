@@ -993,22 +993,42 @@ __device__ static uint64_t rle_pass(const uint8_t *p, uint64_t n, uint8_t *out)
     uint64_t i = 0, o = 0;
     uint32_t last = 0;
     while (i < lim) {
-        const uint64_t pos = i + lane;
-        const uint32_t b = pos < n ? p[pos] : 1u;
-        uint32_t nb = __shfl_down_sync(FULL, b, 1);
-        if (lane == 31) nb = pos + 1 < n ? p[pos + 1] : 1u;
-        const bool cand = pos < lim && b == nb && (b == 0 || b == 0xff);
-        const uint32_t mask = __ballot_sync(FULL, cand);
-        const uint32_t k = mask ? (uint32_t)__ffs((int)mask) - 1 : 32;
+        /* 256 bytes a step, eight to a lane: the loads of a step are independent of each other, and one step's latency
+           is paid for eight times the bytes of a byte per lane */
+        constexpr int BPL = 8;
+        const uint64_t pos = i + BPL * lane;
+        uint32_t b[BPL + 1];
+#pragma unroll
+        for (int j = 0; j < BPL; j++) b[j] = pos + j < n ? p[pos + j] : 1u;
+        b[BPL] = __shfl_down_sync(FULL, b[0], 1);
+        if (lane == 31) b[BPL] = pos + BPL < n ? p[pos + BPL] : 1u;
+        uint32_t k = 32 * BPL;
+#pragma unroll
+        for (int j = 0; j < BPL; j++) {
+            const bool cand = pos + j < lim && b[j] == b[j + 1] && (b[j] == 0 || b[j] == 0xff);
+            const uint32_t mask = __ballot_sync(FULL, cand);
+            if (mask) k = min(k, BPL * ((uint32_t)__ffs((int)mask) - 1) + j);
+        }
+        auto byte_at = [&](uint32_t idx) -> uint32_t { /* byte idx of the step (warp uniform idx) */
+            const uint32_t j = idx % BPL;
+            uint32_t v = b[0];
+#pragma unroll
+            for (int t = 1; t < BPL; t++) if (j == (uint32_t)t) v = b[t];
+            return __shfl_sync(FULL, v, idx / BPL);
+        };
         const uint32_t nlit = (uint32_t)min((uint64_t)k, lim - i);
         if (nlit) {
-            if (out && lane < nlit) out[o + lane] = (uint8_t)b;
-            last = __shfl_sync(FULL, b, nlit - 1);
+            if (out) {
+#pragma unroll
+                for (int j = 0; j < BPL; j++)
+                    if (BPL * lane + j < nlit) out[o + BPL * lane + j] = (uint8_t)b[j];
+            }
+            last = byte_at(nlit - 1);
             o += nlit;
             i += nlit;
         }
-        if (k == 32) continue;
-        const uint32_t c = __shfl_sync(FULL, b, k); /* the candidate, now at position i */
+        if (k == 32 * BPL) continue;
+        const uint32_t c = byte_at(k); /* the candidate, now at position i */
         if (c == 0xff) {
             if (out && lane < 3) out[o + lane] = 0xff;
             o += 3; i += 2; last = 0;
@@ -1058,7 +1078,15 @@ __global__ void __launch_bounds__(128) rle_kernel(const __grid_constant__ EncArg
         if (rsz <= avail && rsz < data) {
             rle_pass(dst + hdr, data, dst + len); /* into the free tail of the slot, then down over the data */
             __syncwarp();
-            for (uint64_t k = lane; k < rsz; k += 32) dst[hdr + k] = dst[len + k];
+            /* down over the data; eight bytes a lane and step, loads before stores (the ranges do not overlap within a
+               step: the source is at least the data's length further on) */
+            for (uint64_t k0 = 0; k0 < rsz; k0 += 256) {
+                uint8_t t[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const uint64_t k = k0 + 8 * lane + j; t[j] = k < rsz ? dst[len + k] : 0; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const uint64_t k = k0 + 8 * lane + j; if (k < rsz) dst[hdr + k] = t[j]; }
+            }
             if (lane == 0) {
                 dst[10] = (uint8_t)a.rle_mode;
                 a.sizes[tile] = hdr + rsz;

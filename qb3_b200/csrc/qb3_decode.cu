@@ -1990,20 +1990,29 @@ __global__ void __launch_bounds__(128) derle_kernel(const DecArgs a, uint8_t *xb
         uint64_t i = 0, o = 0;
         bool fits = true;
         while (i < plen && fits) {
-            const uint64_t pos = i + lane;
-            const uint32_t b = pos < plen ? p[pos] : 0u;
-            uint32_t nx = __shfl_down_sync(FULL, b, 1);
-            if (lane == 31) nx = pos + 1 < plen ? p[pos + 1] : 0u;
-            const bool cand = b == 0xff && nx == 0xff && pos + 2 < plen;
-            const uint32_t mask = __ballot_sync(FULL, cand);
-            const uint32_t k = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
+            constexpr int BPL = 8; /* bytes per lane and step: independent loads, one latency for 256 bytes */
+            const uint64_t pos = i + BPL * lane;
+            uint32_t b[BPL + 1];
+#pragma unroll
+            for (int j = 0; j < BPL; j++) b[j] = pos + j < plen ? p[pos + j] : 0u;
+            b[BPL] = __shfl_down_sync(FULL, b[0], 1);
+            if (lane == 31) b[BPL] = pos + BPL < plen ? p[pos + BPL] : 0u;
+            uint32_t k = 32 * BPL;
+#pragma unroll
+            for (int j = 0; j < BPL; j++) {
+                const bool cand = b[j] == 0xff && b[j + 1] == 0xff && pos + j + 2 < plen;
+                const uint32_t mask = __ballot_sync(FULL, cand);
+                if (mask) k = min(k, BPL * ((uint32_t)__ffs((int)mask) - 1) + j);
+            }
             const uint32_t nlit = (uint32_t)min((uint64_t)k, plen - i);
-            fits = o + 32 + 260 <= cap;
+            fits = o + 32 * BPL + 260 <= cap;
             if (!fits) break;
-            if (lane < nlit) out[o + lane] = (uint8_t)b;
+#pragma unroll
+            for (int j = 0; j < BPL; j++)
+                if (BPL * lane + j < nlit) out[o + BPL * lane + j] = (uint8_t)b[j];
             o += nlit;
             i += nlit;
-            if (k == 32) continue;
+            if (k == 32 * BPL) continue;
             const uint32_t c = p[i + 2];
             if (c == 0xff) {
                 if (lane < 2) out[o + lane] = 0xff;
@@ -2039,7 +2048,7 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a0, cuda
     uint8_t *xscratch = nullptr;
     if (a.rle_hint && a.w >= 4 && a.h >= 4) {
         /* room for every stream expanded: what qb3_max_encoded_size allows, the headers, alignment */
-        const uint64_t xslot = ((1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) * 8 + 2) / 8 + 2048 + 64) + 15) & ~15ull;
+        const uint64_t xslot = ((1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) * 8 + 2) / 8 + 2048 + 1024) + 15) & ~15ull;
         const size_t idx_bytes = ((size_t)a.ntiles * 16 + 15) & ~(size_t)15;
         cudaMemPool_t pool = scratch_pool();
         err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&xscratch), idx_bytes + xslot * a.ntiles, pool, st)

@@ -91,8 +91,10 @@ LIBQB3_EXPORT int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src,
                                      uint64_t *d_state, size_t ntiles, void *stream);
 
 /*
- * Decodes ntiles streams whose headers must all describe width x height x bands of dtype (cfg->mode,
- * quanta, order and cband are read from each stream's own header, cfg->stride is the output stride).
+ * Decodes ntiles streams whose headers must all describe width x height x bands of dtype (mode, quanta,
+ * order and cband are read from each stream's own header, cfg->stride is the output stride). cfg->mode is
+ * only a hint: when it names an RLE mode (2, 3, 6, 7 -- QB3M_BEST is 7), room is set aside to expand RLE
+ * streams ahead of the parallel decode; without the hint RLE streams still decode, on a slow path.
  *   d_streams        base pointer; stream t occupies [d_offsets[t], d_offsets[t] + d_lens[t])
  *   d_dst            tile t is written at d_dst + t * dst_tile_pitch bytes
  *   d_status[t]      QB3CU_TILE_* ; the tile content is undefined unless QB3CU_TILE_OK

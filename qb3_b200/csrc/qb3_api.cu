@@ -316,6 +316,7 @@ size_t qb3_read_data(decsp p, void *destination)
         p->error = QB3E_EINV;
         return 0;
     }
+    if (p->mode >= 0 && p->mode < QB3M_END) c.mode = (uint32_t)p->mode; /* an RLE stream: expanded ahead of the parallel decode */
     const size_t ts = TSIZE[p->type], line = p->xsize * p->nbands * ts, out = line * p->ysize;
     const size_t pitch = (p->stride ? p->stride : p->xsize * p->nbands) * ts;
     if (pitch < line) { p->error = QB3E_EINV; return 0; }

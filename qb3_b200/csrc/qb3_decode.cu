@@ -2024,6 +2024,9 @@ __global__ void __launch_bounds__(128) derle_kernel(const DecArgs a, uint8_t *xb
             }
             i += 3;
         }
+        /* an expanded payload larger than the raw image is refused by the reference (QB3decode.cpp:398-404): such a
+           stream keeps its place, and the general path reports it */
+        if (o > ((uint64_t)a.w * a.h * a.bands << (a.dtype >> 1))) fits = false;
         if (fits) {
             for (uint32_t j = lane; j < 8; j += 32) out[o + j] = 0; /* the readers look a word past the end */
             for (uint32_t j = lane; j < hdr; j += 32) head[j] = j == 10 ? (uint8_t)(info.mode - 2) : stream[j];

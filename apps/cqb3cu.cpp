@@ -474,14 +474,57 @@ static int encode_folder(const Options &opt)
     return rc;
 }
 
+/* folder mode, decoding: streams of the same geometry and type as one batch through the host pipeline */
 static int decode_folder(const Options &opt)
 {
+    struct Item { string name; vector<uint8_t> bytes; };
+    struct Key { size_t w, h, b; int dt; bool operator<(const Key &o) const { return tie(w, h, b, dt) < tie(o.w, o.h, o.b, o.dt); } };
+    map<Key, vector<Item>> groups;
     int rc = 0;
     for (auto &e : fs::directory_iterator(opt.in_fname)) {
         string ext = e.path().extension().string();
         transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
         if (ext != ".qb3") continue;
-        rc |= decode_file(opt, e.path().string(), out_name(opt, e.path().string(), opt.raw_spec.empty() ? ".pnm" : ".raw"));
+        Item it;
+        it.name = e.path().string();
+        size_t sz[3];
+        decsp q = read_file(it.name, it.bytes) ? qb3_read_start(it.bytes.data(), it.bytes.size(), sz) : nullptr;
+        if (!q || !qb3_read_info(q)) { cerr << it.name << " is not a QB3 stream\n"; rc = 1; if (q) qb3_destroy_decoder(q); continue; }
+        const Key k{sz[0], sz[1], sz[2], (int)qb3_get_type(q)};
+        qb3_destroy_decoder(q);
+        groups[k].push_back(std::move(it));
+    }
+    const string ext_out = opt.raw_spec.empty() ? ".pnm" : ".raw";
+    for (auto &g : groups) {
+        auto &items = g.second;
+        const size_t n = items.size();
+        Image im;
+        im.w = g.first.w; im.h = g.first.h; im.bands = g.first.b; im.dt = (qb3_dtype)g.first.dt;
+        const size_t tile = im.w * im.h * im.bands * TSIZE[im.dt];
+        qb3cu_config cfg;
+        qb3cu_config_init(&cfg, (uint32_t)im.w, (uint32_t)im.h, (uint32_t)im.bands, (uint32_t)im.dt);
+        cfg.mode = QB3M_BEST; /* only a hint for the decoder: RLE streams may be among them */
+        vector<uint64_t> offs(n), lens(n);
+        uint64_t total = 0;
+        for (size_t i = 0; i < n; i++) { offs[i] = total; lens[i] = items[i].bytes.size(); total += (lens[i] + 15) & ~(uint64_t)15; }
+        uint8_t *h_streams = static_cast<uint8_t *>(qb3cu_host_alloc(total + 16)), *h_px = static_cast<uint8_t *>(qb3cu_host_alloc(n * tile));
+        qb3cu_pipe *pipe = qb3cu_pipe_create(&cfg, 0, 0);
+        if (!h_streams || !h_px || !pipe) { cerr << "Can't set the batch up (no CUDA device?)\n"; return 2; }
+        for (size_t i = 0; i < n; i++) memcpy(h_streams + offs[i], items[i].bytes.data(), lens[i]);
+        vector<uint32_t> status(n, 0);
+        const auto t1 = chrono::high_resolution_clock::now();
+        const int r = qb3cu_pipe_decode(pipe, h_streams, offs.data(), lens.data(), h_px, tile, status.data(), 0, n);
+        const double s = chrono::duration<double>(chrono::high_resolution_clock::now() - t1).count();
+        if (r) { cerr << "Batch decode failed\n"; rc = 2; }
+        for (size_t i = 0; i < n && !r; i++) {
+            if (status[i] != QB3CU_TILE_OK) { cerr << items[i].name << ": decoding failed\n"; rc = 2; continue; }
+            im.px.assign(h_px + i * tile, h_px + (i + 1) * tile);
+            if (!write_image(out_name(opt, items[i].name, ext_out), im, !opt.raw_spec.empty())) rc = 1;
+        }
+        if (opt.verbose)
+            cout << n << " streams " << im.w << "x" << im.h << "@" << im.bands << ": " << n * tile / s / 1024 / 1024 << " MB/s\n";
+        qb3cu_pipe_destroy(pipe);
+        qb3cu_host_free(h_streams); qb3cu_host_free(h_px);
     }
     return rc;
 }

@@ -413,6 +413,12 @@ def test_cli_encode_decode_bandmix_and_folder(tmp_path):
     for t in range(3):
         assert (o / ("t%d.qb3" % t)).read_bytes() == oracle().encode(rgb[t], mode=MODE_FTL)
     assert (o / "g.qb3").read_bytes() == oracle().encode(gray16, mode=MODE_FTL)
+    # and back: the folder of streams decoded as batches per geometry
+    back = tmp_path / "back"; back.mkdir()
+    r = run("-d", str(o), str(back)); assert r.returncode == 0, r
+    for t in range(3):
+        assert (back / ("t%d.pnm" % t)).read_bytes() == (d / ("t%d.ppm" % t)).read_bytes()
+    assert (back / "g.pnm").read_bytes() == (d / "g.pgm").read_bytes()
 
 
 def test_two_pipes_on_two_threads():

@@ -322,35 +322,63 @@ template <typename W> struct IndexTable {
             seen |= 1ull << ((h * 0x9E3779B1u) >> 26);
         }
         if (__popcll(seen) > 8) return false;
+        /* Everything below indexes the table with compile time constants only (unrolled, predicated), so that it
+           lives in registers: with run time indices it sat in local memory and the threads that came this far kept
+           the rest of their CTA waiting at the next barrier (35 % of the stall samples of the BEST encoder). */
+#pragma unroll
+        for (int k = 0; k < 8; k++) { val[k] = 0; cnt[k] = 0; }
         n = 0;
+        uint64_t first = 0; /* 16 x 3 bits: the first-seen index of value i */
+#pragma unroll
         for (int i = 0; i < 16; i++) {
-            uint32_t j = 0;
-            while (j < n && val[j] != m[i]) j++;
-            if (j == n) {
+            uint32_t hit = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) hit |= (uint32_t)(cnt[k] != 0 && val[k] == m[i]) << k;
+            if (hit == 0) {
                 if (n == 8) return false;
-                val[n] = m[i]; cnt[n] = 1; n++;
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (k == (int)n) { val[k] = m[i]; cnt[k] = 1; }
+                first |= (uint64_t)n << (3 * i);
+                n++;
             }
-            else cnt[j]++;
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) cnt[k] += (hit >> k) & 1;
+                first |= (uint64_t)((uint32_t)__ffs((int)hit) - 1) << (3 * i);
+            }
         }
-        for (uint32_t i = 1; i < n; i++)
-            for (uint32_t j = i; j > 0 && cnt[j] > cnt[j - 1]; j--) {
-                const W tv = val[j]; val[j] = val[j - 1]; val[j - 1] = tv;
-                const uint32_t tc = cnt[j]; cnt[j] = cnt[j - 1]; cnt[j - 1] = tc;
+        /* stable, by descending count: adjacent exchanges on strictly greater only (unused entries count 0 and stay
+           behind); id[k] = first-seen index of the entry now at k */
+        uint32_t id[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) id[k] = k;
+#pragma unroll
+        for (int pass = 0; pass < 7; pass++) {
+#pragma unroll
+            for (int j = 7; j > pass; j--) {
+                if (cnt[j] > cnt[j - 1]) {
+                    const W tv = val[j]; val[j] = val[j - 1]; val[j - 1] = tv;
+                    const uint32_t tc = cnt[j]; cnt[j] = cnt[j - 1]; cnt[j - 1] = tc;
+                    const uint32_t ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
+                }
             }
+        }
+        uint32_t where = 0; /* 8 x 3 bits: the slot of the entry first seen as number f */
+#pragma unroll
+        for (int k = 0; k < 8; k++) where |= (uint32_t)k << (3 * id[k]);
         slots = 0;
-        for (int i = 0; i < 16; i++) {
-            uint32_t j = 0;
-            while (val[j] != m[i]) j++;
-            slots |= (uint64_t)j << (3 * i);
-        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) slots |= (uint64_t)((where >> (3 * ((uint32_t)(first >> (3 * i)) & 7))) & 7) << (3 * i);
         return true;
     }
     /* bits after the three prefix fields */
     __device__ uint32_t payload_len(uint32_t rung) const
     {
         uint32_t len = 0;
+#pragma unroll
         for (int i = 0; i < 16; i++) len += code_len<uint32_t>((uint32_t)(slots >> (3 * i)) & 7, 2);
-        for (uint32_t j = 0; j < n; j++) len += single_len<W>(val[j], rung);
+#pragma unroll
+        for (int j = 0; j < 8; j++) if ((uint32_t)j < n) len += single_len<W>(val[j], rung);
         return len;
     }
 };
@@ -797,7 +825,8 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
                         const uint32_t l = code_bits<uint32_t>((uint32_t)(tb.slots >> (3 * i)) & 7, 2, lo, hi);
                         pk.put32((uint32_t)lo, l); /* no middle swap, reference: QB3encode.h:599-601 */
                     }
-                    for (uint32_t j = 0; j < tb.n; j++) VP::put_single(pk, tb.val[j], rung);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if ((uint32_t)j < tb.n) VP::put_single(pk, tb.val[j], rung);
                 }
             }
             else if (BEST && active && bitsused > 1) { /* plain group, always with step coding */

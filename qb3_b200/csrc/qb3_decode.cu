@@ -713,12 +713,9 @@ struct RowChunk {
     uint32_t first, last;
 };
 
-/* How a scan launch is laid out: several warps to a CTA, each with its own slice of shared memory; and whether the
-   launch walks its block rows as 'inner' sub-chunks, reporting each at flags[j]. */
+/* How a scan launch is laid out: several warps to a CTA, each with its own slice of shared memory. */
 struct ScanPlan {
     uint32_t warp_smem; /* bytes of shared memory per warp, multiple of 16 */
-    uint32_t inner;     /* >= 1 */
-    uint32_t *flags;    /* null, or inner counters */
 };
 
 /*
@@ -896,11 +893,7 @@ __global__ void __launch_bounds__(128, 1) scan_kernel(const DecArgs a, uint32_t 
 
     const uint32_t per_row = ((a.w + 3) / 4) * bands;
     uint32_t c = 0, upkeep = 1;
-    /* plan.inner > 1: this launch walks all the row chunks itself and counts a warp in at flags[j] when its streams
-       are through chunk j; the host has queued the rebuild of chunk j behind a wait on that counter */
-    for (uint32_t j = 0; j < plan.inner; j++) {
-    const uint32_t g_begin = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * j / plan.inner)) * per_row,
-                   g_end = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * (j + 1) / plan.inner)) * per_row;
+    const uint32_t g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
     for (uint32_t g = g_begin; g < g_end; g++) {
         /* ring upkeep every few groups: request chunks up to AHEAD beyond the one being read. What was requested one
            upkeep ago has had EVERY groups to land and is waited for; the new requests are for reads two upkeeps away. */
@@ -973,12 +966,6 @@ __global__ void __launch_bounds__(128, 1) scan_kernel(const DecArgs a, uint32_t 
         rb[c * 32 + lane] = (uint8_t)r;
         if (go) rec[g] = (pos << 4) | r;
         c = c + 1 == bands ? 0 : c + 1;
-    }
-    if (plan.flags) {
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(plan.flags + j, 1u);
-    }
     }
     cp_async_wait<0>();
     if (go && ch.last) {
@@ -1096,9 +1083,7 @@ __global__ void __launch_bounds__(128, 1) scan_wide_kernel(const DecArgs a, uint
     uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
     const uint32_t per_row = ((a.w + 3) / 4) * bands;
     uint32_t c = 0, upkeep = 1;
-    for (uint32_t j = 0; j < plan.inner; j++) { /* see scan_kernel */
-    const uint32_t g_begin = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * j / plan.inner)) * per_row,
-                   g_end = (ch.by0 + (uint32_t)((uint64_t)(ch.by1 - ch.by0) * (j + 1) / plan.inner)) * per_row;
+    const uint32_t g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
     for (uint32_t g = g_begin; g < g_end; g++) {
         if (--upkeep == 0) {
             upkeep = EVERY;
@@ -1140,12 +1125,6 @@ __global__ void __launch_bounds__(128, 1) scan_wide_kernel(const DecArgs a, uint
         rb[c * 32 + lane] = (uint8_t)r;
         if (go) rec[g] = (pos << 6) | r;
         c = c + 1 == bands ? 0 : c + 1;
-    }
-    if (plan.flags) {
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(plan.flags + j, 1u);
-    }
     }
     cp_async_wait<0>();
     if (go && ch.last) {
@@ -1786,20 +1765,26 @@ cudaMemPool_t scratch_pool()
 static cudaStream_t aux_stream(cudaStream_t user, bool high)
 {
     struct Slot { cudaStream_t user, aux; bool used, high; };
-    static Slot slots[64][64] = {};
+    static Slot slots[64][128] = {};
+    static cudaStream_t shared[64][2] = {}; /* for the callers that come when the table is full, one per kind */
     static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lock(mu);
-    Slot *free_slot = nullptr, *same_kind = nullptr;
-    for (Slot &sl : slots[dev]) {
-        if (sl.used && sl.user == user && sl.high == high) return sl.aux;
-        if (sl.used && sl.high == high && !same_kind) same_kind = &sl;
-        if (!sl.used && !free_slot) free_slot = &sl;
-    }
-    if (!free_slot) return same_kind ? same_kind->aux : nullptr; /* more caller streams than slots: share one */
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    Slot *free_slot = nullptr;
+    for (Slot &sl : slots[dev]) {
+        if (sl.used && sl.user == user && sl.high == high) return sl.aux;
+        if (!sl.used && !free_slot) free_slot = &sl;
+    }
+    if (!free_slot) {
+        /* Streams come and go (every QB3.h handle has its own) and the table never forgets: once it is full, later
+           callers share one stream per kind. Their batches then queue behind each other there, which is only slower. */
+        cudaStream_t &sh = shared[dev][high ? 1 : 0];
+        if (!sh && cudaStreamCreateWithPriority(&sh, cudaStreamNonBlocking, high ? greatest : least) != cudaSuccess) sh = nullptr;
+        return sh;
+    }
     if (cudaStreamCreateWithPriority(&free_slot->aux, cudaStreamNonBlocking, high ? greatest : least) != cudaSuccess) return nullptr;
     free_slot->user = user;
     free_slot->used = true;
@@ -1908,7 +1893,7 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     };
     if (err == cudaSuccess && nchunks > 1) err = order_after(aux, st); /* the streams and the scratch memory are ready */
     ScanPlan plan;
-    plan.warp_smem = (uint32_t)smem1; plan.inner = 1; plan.flags = nullptr;
+    plan.warp_smem = (uint32_t)smem1;
     /* Chunk sizes shrink geometrically: the rebuild of a chunk takes about 0.8 of its scan's time and cannot start
        before that scan is over, so with each chunk 0.8 of the one before, every rebuild ends as the next scan does and
        what is left after the last scan is the rebuild of a sliver (equal chunks leave a sixteenth of the rebuild). */

@@ -537,3 +537,33 @@ def test_damaged_streams_decode_like_the_oracle(dt, mode):
             assert np.array_equal(out_h[t], want), "tile %d decodes differently" % t
             agree += 1
     assert agree > 0
+
+
+def test_many_caller_streams():
+    """Every caller stream gets helper streams inside the decoder, remembered in a table that never forgets; more
+    caller streams than the table holds (QB3.h handles come and go by the hundred) must still decode, on either kind of
+    helper stream (scans on their own SMs for a lone tile, shared SMs inside the host pipeline)."""
+    torch = torch_mod()
+    n, w, h, b = 4, 64, 64, 3
+    tiles = synth_tiles(n, w, h, b, np.uint8)
+    cfg, dst, sizes, status = encode_tiles(tiles, mode=MODE_BASE)
+    offsets = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+    streams = [torch.cuda.Stream() for _ in range(200)]   # kept alive: two hundred distinct handles
+    outs = []
+    for st in streams:
+        with torch.cuda.stream(st):
+            st.wait_stream(torch.cuda.current_stream())
+            out, s1 = q.decode_batch(cfg, dst, offsets[:1], sizes[:1], 1, stream=st)
+            outs.append((out, s1))
+    torch.cuda.synchronize()
+    for out, s1 in outs[::17]:
+        assert not s1.cpu().numpy().any() and np.array_equal(out.cpu().numpy().reshape(1, h, w, b)[0], tiles[0])
+    pipe = q.Pipe(cfg, 2, 2)
+    packed = np.zeros(n * q.slot_bytes(cfg), np.uint8)
+    off, sz = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    pipe.encode(tiles, n, packed, off, sz)
+    back = np.zeros_like(tiles)
+    stat = np.full(n, 9, np.uint32)
+    pipe.decode(packed, off, sz, n, back, stat)
+    assert not stat.any() and np.array_equal(back, tiles)
+    pipe.close()

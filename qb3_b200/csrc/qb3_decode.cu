@@ -178,55 +178,12 @@ __device__ static uint64_t derle_size(const uint8_t *p, uint64_t len)
 }
 
 
-/*
- * Bit buffer of the walk kernel (8 and 16 bit types): 64 bits of look-ahead in registers fed one 32 bit word at a
- * time from the stream's ring in shared memory, with one word of read-ahead so the shared memory latency stays off
- * the parse chain. After refill() at least 33 bits are valid, which covers every field of these types (a code is at
- * most 17 bits). All lanes that share a stream hold the same state.
- */
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-
-struct WalkBits {
-    uint64_t buf;
-    uint32_t ring;     /* shared memory address of the stream's ring */
-    uint32_t nb, nxt, k, ringmask, w0, sh;
-
-    __device__ __forceinline__ void open(uint32_t ring_addr, uint32_t mask, uint32_t mis)
-    {
-        ring = ring_addr; ringmask = mask;
-        w0 = mis >> 2; sh = 8 * (mis & 3);
-        buf = (uint64_t)(lds32(ring + 4 * w0) >> sh);
-        nb = 32 - sh;
-        buf |= (uint64_t)lds32(ring + 4 * (w0 + 1)) << nb;
-        nb += 32;
-        nxt = lds32(ring + 4 * (w0 + 2));
-        k = w0 + 3;
-    }
-    __device__ __forceinline__ void refill()
-    {
-        if (nb <= 32) {
-            buf |= (uint64_t)nxt << nb;
-            nb += 32;
-            nxt = lds32(ring + 4 * (k & ringmask));
-            k++;
-        }
-    }
-    __device__ __forceinline__ uint64_t peek() { refill(); return buf; }
-    __device__ __forceinline__ void advance(uint32_t n) { buf >>= n; nb -= n; } /* n <= 33, after peek() / refill() */
-    __device__ __forceinline__ uint64_t get(uint32_t n)
-    {
-        refill();
-        const uint64_t v = buf & lowmask64(n);
-        advance(n);
-        return v;
-    }
-    __device__ __forceinline__ uint64_t consumed() const { return 32ull * (k - 1 - w0) - sh - nb; }
-};
 
 /* dequantize (reference: QB3decode.cpp:77-107): multiply by quanta, saturating at the type's range */
 template <int BITS> __device__ __forceinline__ uint64_t dequantize_value(uint64_t v, uint64_t q, bool is_signed)
@@ -376,332 +333,6 @@ __device__ __noinline__ bool read_special_group(S &s, W (&g)[16], uint8_t &rb, W
     return failed;
 }
 
-/*
- * The decode kernel for 8 and 16 bit types: a warp walks 32 / LPS streams, LPS lanes each.
- *
- * A stream is one serial bit parse (every code's position depends on the two low bits of the code before it and
- * there is no index in the format), so what bounds a stream is the latency of that chain, and what bounds the
- * batch is how many streams are in flight and how few issue slots each one takes. Hence:
- *  - the lanes of a stream all run the chain (the same instructions, so the redundancy is free) and keep only the
- *    codes of their own 16 / LPS values; values, step undo, sign unfolding, the running sum (a shuffle scan) and
- *    the scatter into the staged rows are then split between the lanes
- *  - the compressed bytes travel HBM -> registers -> shared memory ring in 16 byte units per lane, half a ring
- *    ahead of the parse position, so no global load latency is ever on the chain
- *  - pixels are staged per stream for a run of blocks (four image rows). The core band is added while staging
- *    (QB3decode.h:730-737): a lane owns the same pixels in every band of a block, so a derived band that comes after
- *    its core band adds the staged core value, and a core band adds itself to the derived bands staged before it.
- *    Quanta are multiplied at the flush (QB3decode.cpp:77-107); rows leave as whole 16 byte vectors
- * Streams this kernel does not take (stored, RLE, bad headers) are left to the general path through the tile status.
- */
-template <typename T, int LPS>
-__global__ void __launch_bounds__(32, 16) walk_kernel(const DecArgs a, const uint32_t stage_blocks, const uint32_t stage_off,
-                                                  const uint32_t sstride)
-{
-    typedef uint32_t W;
-    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
-    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
-    constexpr W TM = (W)((1ull << BITS) - 1);
-    constexpr int NS = 32 / LPS, VPL = 16 / LPS, HW = 4 * LPS, RW = 2 * HW;
-    constexpr int VPR = BITS == 8 ? 3 : 2; /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
-    constexpr int MAXWORDS = BITS == 8 ? 6 : 12; /* ring words one group can consume, any kind */
-    constexpr int UPKEEP = (HW - 2) / MAXWORDS > 0 ? (HW - 2) / MAXWORDS : 1; /* groups between ring checks */
-    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xff;
-
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t *dsw = reinterpret_cast<uint16_t *>(smem); /* rung switch decode table, 2^(U+1) entries */
-    const uint32_t lane = threadIdx.x, sub = lane / LPS, sl = lane % LPS;
-    const uint32_t submask = LPS == 32 ? FULL : ((1u << LPS) - 1) << (sub * LPS);
-    const uint32_t bands = a.bands;
-    uint8_t *mine = smem + 64 + (size_t)sub * sstride;
-    uint32_t *ring = reinterpret_cast<uint32_t *>(mine);
-    uint32_t *prev = ring + RW, *pcf = prev + bands;
-    uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + bands), *cb = rb + bands;
-    uint8_t *head = cb + bands, *nextc = head + bands; /* derived bands that precede their core band, as lists */
-    T *stage = reinterpret_cast<T *>(mine + stage_off);
-    const bool staged = stage_blocks != 0;
-
-    for (uint32_t i = lane; i < (2u << U); i += 32) dsw[i] = (uint16_t)ds_entry(U, i);
-
-    const uint32_t tile = blockIdx.x * NS + sub;
-    const bool live = tile < a.ntiles;
-    const uint8_t *stream = nullptr;
-    uint64_t slen = 0;
-    StreamInfo info;
-    info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
-    uint32_t bandflags = 0; /* 1: some band is derived, 2: a core band is itself derived (only hand made streams) */
-    if (live) {
-        stream = a.streams + a.offsets[tile];
-        slen = a.lens[tile];
-        if (sl == 0) {
-            parse_header(stream, slen, a, info, cb, 1);
-            for (uint32_t c = 0; c < bands; c++) head[c] = nextc[c] = (uint8_t)NONE;
-            for (uint32_t c = bands; c-- > 0;) {
-                const uint32_t k = cb[c];
-                if (k != c) bandflags |= 1 | (cb[k] != k ? 2 : 0);
-                if (k > c) { nextc[c] = head[k]; head[k] = (uint8_t)c; }
-            }
-        }
-    }
-    __syncwarp();
-    info.bad = __shfl_sync(FULL, info.bad, 0, LPS);
-    info.mode = __shfl_sync(FULL, info.mode, 0, LPS);
-    info.data_off = __shfl_sync(FULL, info.data_off, 0, LPS);
-    info.order = __shfl_sync(FULL, info.order, 0, LPS);
-    info.quanta = __shfl_sync(FULL, info.quanta, 0, LPS);
-    bandflags = __shfl_sync(FULL, bandflags, 0, LPS);
-    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
-    const bool go = live && !info.bad && info.mode != M_STORED && !rle;
-    if (live && !go && sl == 0) a.status[tile] = info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
-
-    /* the payload as 16 byte chunks from an aligned base; bytes past the end read as zero (bitstream.h:43-49) */
-    const uint8_t *payload = go ? stream + info.data_off : nullptr;
-    const uint64_t plen = go ? slen - info.data_off : 0;
-    const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
-    const uint8_t *abase = payload - mis;
-    const uint64_t span = go ? mis + plen : 0;
-    auto load_chunk = [&](uint32_t ci) -> uint4 {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        const uint64_t start = 16ull * ci;
-        if (start < span) {
-            v = ld_stream16(abase + start);
-            if (start + 16 > span) {
-                const uint32_t rem = (uint32_t)(span - start); /* 1..15 valid bytes */
-                uint32_t *w = reinterpret_cast<uint32_t *>(&v);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t lo = 4 * j;
-                    if (rem <= lo) w[j] = 0;
-                    else if (rem < lo + 4) w[j] &= (1u << (8 * (rem - lo))) - 1;
-                }
-            }
-        }
-        return v;
-    };
-
-    for (uint32_t c = sl; c < bands; c += LPS) { prev[c] = 0; pcf[c] = 0; rb[c] = 0; }
-    uint4 *ring4 = reinterpret_cast<uint4 *>(ring);
-    ring4[sl] = load_chunk(sl);
-    ring4[LPS + sl] = load_chunk(LPS + sl);
-    uint4 pend = load_chunk(2 * LPS + sl);
-    uint32_t curhalf = 0;
-    __syncwarp();
-
-    const uint64_t quanta = info.quanta;
-    const bool is_signed = a.dtype & 1;
-    const bool add_inline = go && staged && bandflags == 1;        /* the usual case: core bands are not derived */
-    const bool fix_bands = go && staged && (bandflags & 2);        /* chained band maps: the reference's sweep, at the flush */
-    const bool fix = go && staged && ((bandflags & 2) || quanta > 1);
-    const bool any_step = __any_sync(FULL, go && info.mode != M_FTL);
-    const bool any_fix = __any_sync(FULL, fix); /* warp uniform: the branches below contain warp barriers */
-
-    WalkBits s;
-    s.open((uint32_t)__cvta_generic_to_shared(ring), RW - 1, mis);
-
-    const uint64_t order = info.order ? info.order : HILBERT;
-    const bool ftl = info.mode == M_FTL;
-    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4;
-    const uint32_t sblocks = staged ? stage_blocks : 1;
-    const uint32_t rowelems = staged ? stage_blocks * 4 * bands : (uint32_t)a.stride;
-    uint32_t off[VPL];
-#pragma unroll
-    for (int j = 0; j < VPL; j++) {
-        const uint32_t n = (uint32_t)(order >> (4 * (15 - (sl * VPL + j)))) & 15;
-        off[j] = (n >> 2) * rowelems + (n & 3) * bands;
-    }
-    T *out = reinterpret_cast<T *>(a.dst + (uint64_t)(live ? tile : 0) * a.dst_pitch);
-
-    bool failed = false;
-    uint32_t upkeep = 1;
-    for (uint32_t by = 0; by < nby; by++) {
-        const uint32_t y0 = min(4 * by, a.h - 4);
-        for (uint32_t gb = 0; gb < nbx; gb += sblocks) {
-            const uint32_t gend = min(nbx, gb + sblocks);
-            const uint32_t xs = min(4 * gb, a.w - 4), xe = min(4 * gend, a.w);
-            for (uint32_t bx = gb; bx < gend; bx++) {
-                const uint32_t x0 = min(4 * bx, a.w - 4);
-                for (uint32_t c = 0; c < bands; c++) {
-                    /* ring upkeep every few groups: on entering a half, the chunks held back in registers replace the
-                       half just left and the loads for the half after that start */
-                    if (--upkeep == 0) {
-                        upkeep = UPKEEP;
-                        const uint32_t hnow = s.k / HW;
-                        if (hnow != curhalf) {
-                            curhalf = hnow;
-                            __syncwarp(submask);
-                            ring4[((hnow + 1) & 1) * LPS + sl] = pend;
-                            pend = load_chunk((hnow + 2) * LPS + sl);
-                            __syncwarp(submask);
-                        }
-                    }
-                    const W pv = prev[c];
-                    const uint32_t oldrung = rb[c], kc = cb[c], hc = head[c];
-
-                    s.refill();
-                    const uint32_t x = (uint32_t)s.buf;
-                    uint32_t cs = 0;
-                    if (x & 1) cs = dsw[(x >> 1) & LMASK];
-                    s.advance((x & 1) ? cs >> 12 : 1);
-
-                    W v[VPL];
-                    uint32_t r = 0;
-                    bool want_step = false;
-                    if (ftl || (cs & 0xfff) != 0 || cs == 0) {
-                        r = (oldrung + cs) & UMASK;
-                        rb[c] = (uint8_t)r;
-                        if (r == 0) { /* flag, then 16 raw bits (reference: QB3decode.h:148-160) */
-                            s.refill();
-                            const uint32_t y = (uint32_t)s.buf;
-                            const uint32_t b = (y & 1) ? (y >> 1) & 0xffffu : 0u;
-                            s.advance((y & 1) ? 17 : 1);
-#pragma unroll
-                            for (int j = 0; j < VPL; j++) v[j] = (b >> (sl * VPL + j)) & 1;
-                        }
-                        else {
-                            uint32_t code[VPL];
-#pragma unroll
-                            for (int j = 0; j < VPL; j++) code[j] = 0;
-                            if (BITS == 16 && r == 15) { /* two 17 bit codes exceed what one refill promises */
-#pragma unroll
-                                for (int i = 0; i < 16; i++) {
-                                    s.refill();
-                                    const uint32_t lo = (uint32_t)s.buf;
-                                    const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
-                                    if (sl == i / VPL) code[i % VPL] = lo;
-                                    s.advance(r + b0 + t);
-                                }
-                            }
-                            else {
-#pragma unroll
-                                for (int i = 0; i < 16; i++) {
-                                    if (i % VPR == 0) s.refill();
-                                    const uint32_t lo = (uint32_t)s.buf;
-                                    const uint32_t b0 = lo & 1, t = b0 & (lo >> 1);
-                                    if (sl == i / VPL) code[i % VPL] = lo;
-                                    s.advance(r + b0 + t);
-                                }
-                            }
-                            const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
-#pragma unroll
-                            for (int j = 0; j < VPL; j++) {
-                                const uint32_t y = code[j], b0 = y & 1, t = b0 & (y >> 1), ht = half << t;
-                                uint32_t val = ((y >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
-                                if (val - fm1 <= 1u) val ^= sm; /* middle swap at rungs 1..7 */
-                                v[j] = val;
-                            }
-                            want_step = !ftl;
-                        }
-                    }
-                    else { /* common factor or index group: every lane parses it, then keeps its own values */
-                        W sg[16];
-                        uint8_t rbv = (uint8_t)oldrung;
-                        W pc = pcf[c];
-                        WalkBits t = s; /* a copy: the reader itself must never have its address taken, it lives in registers */
-                        failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
-                        s = t;
-                        rb[c] = rbv;
-                        pcf[c] = pc;
-#pragma unroll
-                        for (int j = 0; j < VPL; j++) {
-                            W t2 = 0;
-#pragma unroll
-                            for (int i = 0; i < 16; i++) if (sl * VPL + j == i) t2 = sg[i];
-                            v[j] = t2;
-                        }
-                    }
-                    if (any_step) { /* step undo (reference: QB3decode.h:285-289); value i lives in lane i / VPL, slot i % VPL */
-                        uint32_t kk = 0, ok = 1, m[VPL];
-#pragma unroll
-                        for (int j = 0; j < VPL; j++) {
-                            m[j] = (__ballot_sync(FULL, want_step && ((v[j] >> r) & 1)) >> (sub * LPS)) & (LPS == 32 ? FULL : (1u << LPS) - 1);
-                            kk += __popc(m[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < VPL; j++) ok &= m[j] == (1u << ((kk + VPL - 1 - j) / VPL)) - 1;
-                        if (want_step && ok && kk < 16) {
-#pragma unroll
-                            for (int j = 0; j < VPL; j++) if (sl * VPL + j == kk) v[j] ^= 1u << r;
-                        }
-                    }
-
-                    /* undo the running delta: local sums, then an exclusive scan over the stream's lanes */
-                    W acc[VPL], tot = 0;
-#pragma unroll
-                    for (int j = 0; j < VPL; j++) { tot += smag<BITS, W>(v[j]); acc[j] = tot; }
-                    W inc = tot;
-#pragma unroll
-                    for (int d = 1; d < LPS; d <<= 1) {
-                        const W o = __shfl_up_sync(FULL, inc, d, LPS);
-                        if (sl >= d) inc += o;
-                    }
-                    const W base = pv + inc - tot;
-                    prev[c] = (pv + __shfl_sync(FULL, inc, LPS - 1, LPS)) & TM;
-                    if (staged) {
-                        T *p = stage + (size_t)(x0 - xs) * bands + c;
-                        if (add_inline) {
-                            for (uint32_t e = hc; e != NONE; e = nextc[e]) { /* derived bands staged before this, their core band */
-#pragma unroll
-                                for (int j = 0; j < VPL; j++) p[off[j] + e - c] = (T)(p[off[j] + e - c] + base + acc[j]);
-                            }
-                            if (kc < c) { /* derived from a band that is already staged */
-#pragma unroll
-                                for (int j = 0; j < VPL; j++) acc[j] += p[off[j] + kc - c];
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < VPL; j++) p[off[j]] = (T)(base + acc[j]);
-                    }
-                    else if (go) {
-                        T *p = out + (uint64_t)y0 * a.stride + (uint64_t)x0 * bands + c;
-#pragma unroll
-                        for (int j = 0; j < VPL; j++) p[off[j]] = (T)(base + acc[j]);
-                    }
-                }
-            }
-            if (!staged) continue;
-            __syncwarp();
-            const uint32_t npx = xe - xs;
-            if (any_fix) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
-                for (uint32_t r = 0; fix && r < 4; r++)
-                    for (uint32_t px = sl; px < npx; px += LPS) {
-                        T *p = stage + (size_t)r * rowelems + (size_t)px * bands;
-                        if (fix_bands)
-                            for (uint32_t c = 0; c < bands; c++) {
-                                const uint32_t k = cb[c];
-                                if (k != c) p[c] = (T)(p[c] + p[k]);
-                            }
-                        if (quanta > 1)
-                            for (uint32_t c = 0; c < bands; c++)
-                                p[c] = (T)dequantize_value<BITS>((uint64_t)p[c], quanta, is_signed);
-                    }
-                __syncwarp();
-            }
-            if (go) { /* staged rows leave as the widest vectors the destination allows */
-                const uint32_t rowbytes = npx * bands * (uint32_t)sizeof(T), srow = rowelems * (uint32_t)sizeof(T);
-                for (uint32_t r = 0; r < 4; r++) {
-                    uint8_t *gp = reinterpret_cast<uint8_t *>(out + (uint64_t)(y0 + r) * a.stride + (uint64_t)xs * bands);
-                    const uint8_t *sp = reinterpret_cast<const uint8_t *>(stage) + r * srow;
-                    if ((((uintptr_t)gp | rowbytes) & 15) == 0)
-                        for (uint32_t j = 16 * sl; j < rowbytes; j += 16 * LPS)
-                            *reinterpret_cast<uint4 *>(gp + j) = *reinterpret_cast<const uint4 *>(sp + j);
-                    else if ((((uintptr_t)gp | rowbytes) & 3) == 0)
-                        for (uint32_t j = 4 * sl; j < rowbytes; j += 4 * LPS)
-                            *reinterpret_cast<uint32_t *>(gp + j) = *reinterpret_cast<const uint32_t *>(sp + j);
-                    else
-                        for (uint32_t j = sizeof(T) * sl; j < rowbytes; j += sizeof(T) * LPS)
-                            *reinterpret_cast<T *>(gp + j) = *reinterpret_cast<const T *>(sp + j);
-                }
-            }
-            __syncwarp();
-        }
-    }
-    if (go && sl == 0) {
-        const uint64_t total = 8 * plen, used = s.consumed();
-        const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
-        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT
-                             : (!staged && (bandflags || quanta > 1)) ? ST_FINISH : (uint32_t)QB3CU_TILE_OK;
-    }
-}
-
 /* ------------------------------------------------------------------ two pass decode: scan, then rebuild */
 
 constexpr uint32_t ST_PARSED = 0x20000000u;   /* scan_kernel has written all of the tile's group records */
@@ -718,265 +349,10 @@ struct ScanPlan {
     uint32_t warp_smem; /* bytes of shared memory per warp, multiple of 16 */
 };
 
-/*
- * Bit buffer of scan_kernel: one stream per lane. 64 bits of look-ahead in registers, fed a 32 bit word at a time from
- * the lane's own ring in shared memory, one word of read-ahead. The ring is filled by cp.async in 16 byte chunks,
- * many chunks ahead, so neither global nor shared memory latency is on the parse chain. The ring is addressed through
- * the kernel's shared array itself (the compiler then emits LDS and predicates the refill instead of branching: the
- * lanes of a warp refill at different times and must stay together).
- */
-template <int RWORDS> struct ScanBits {
-    uint32_t lo, mid, hi; /* 96 bits of look-ahead; the parse chain only ever reads lo */
-    uint32_t nb, nxt, k, w0, sh;
-
-    __device__ __forceinline__ void open(const uint32_t *ring, uint32_t mis)
-    {
-        w0 = mis >> 2; sh = 8 * (mis & 3);
-        const uint32_t a = ring[w0], b = ring[w0 + 1], c = ring[w0 + 2];
-        lo = __funnelshift_r(a, b, sh);
-        mid = __funnelshift_r(b, c, sh);
-        hi = c >> sh;
-        nb = 96 - sh;
-        nxt = ring[w0 + 3];
-        k = w0 + 4;
-    }
-    /*
-     * Tops the buffer up to at least 64 bits. Called with at least 32 bits in it (every caller consumes at most 32
-     * between two calls), so the new word lands in mid / hi and never in lo: the chain, which reads lo, does not
-     * wait for the refill, and the refill's own dependency (how many bits the last values took) stays off the chain.
-     * A select, not a branch: the lanes of a warp refill at different times, and a divergent branch costs them all
-     * some fifty cycles (measured), seven times per group.
-     */
-    __device__ __forceinline__ void refill(const uint32_t *ring)
-    {
-        const bool take = nb <= 64;
-        const uint32_t cand = ring[k & (RWORDS - 1)]; /* always loaded, kept only when the word before it moves in */
-        const uint64_t x = (uint64_t)(take ? nxt : 0u) << ((nb - 32) & 63);
-        mid |= (uint32_t)x;
-        hi |= (uint32_t)(x >> 32);
-        nb += take ? 32u : 0u;
-        nxt = take ? cand : nxt;
-        k += take ? 1u : 0u;
-    }
-    /* n < 32; it may carry junk above bit 4: funnel shifts in wrap mode only look at the low five bits */
-    __device__ __forceinline__ void shift(uint32_t n)
-    {
-        lo = __funnelshift_r(lo, mid, n);
-        mid = __funnelshift_r(mid, hi, n);
-        hi = __funnelshift_r(hi, 0u, n);
-    }
-    __device__ __forceinline__ void advance(uint32_t n) { shift(n); nb -= n; } /* n < 32, after refill() */
-    __device__ __forceinline__ uint32_t consumed() const { return 32 * (k - 1 - w0) - sh - nb; }
-};
-
-/* the same reader with the ring pointer inside, for the out-of-line parser of the rare groups */
-template <int RWORDS> struct ScanBitsRef {
-    ScanBits<RWORDS> b;
-    const uint32_t *ring;
-    __device__ __forceinline__ uint64_t peek() { b.refill(ring); return (uint64_t)b.lo | ((uint64_t)b.mid << 32); }
-    __device__ __forceinline__ void advance(uint32_t n) { b.advance(n); }
-    __device__ __forceinline__ uint64_t get(uint32_t n) /* n < 32 */
-    {
-        b.refill(ring);
-        const uint64_t v = b.lo & (uint32_t)lowmask64(n);
-        b.advance(n);
-        return v;
-    }
-};
-
 /* 16 bytes global -> shared, the tail beyond nbytes zero filled */
 __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void *gmem, uint32_t nbytes)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gmem), "r"(nbytes) : "memory");
-}
-
-/*
- * Pass one, 8 and 16 bit types: the serial part of decoding and nothing else. One stream per lane walks its groups and
- * only works out where each one starts and which rung its band is at afterwards: a 32 bit record per group,
- * (start bit << 4) | rung. Values are not decoded (common factor groups excepted: their next rung depends on the
- * values, QB3decode.h:664), nothing is reconstructed or stored, so the chain of a stream is as short as it gets:
- * per value two ANDs, an add and a funnel shift. A lone warp per SM issues about one instruction every two cycles, so
- * what a group costs is its instruction count: the rest of this kernel is about keeping that low.
- * rebuild_kernel then decodes all groups of a tile in parallel.
- */
-template <typename T>
-__global__ void __launch_bounds__(128, 1) scan_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
-                                                      const RowChunk ch, uint32_t *__restrict__ sstate, const ScanPlan plan)
-{
-    typedef uint32_t W;
-    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
-    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
-    constexpr int VPR = BITS == 8 ? 3 : 2;       /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
-    constexpr int RWORDS = BITS == 8 ? 64 : 128; /* ring words per lane */
-    constexpr int LSTRIDE = RWORDS + 4;          /* words between the rings of two lanes: 16 byte multiple, banks shifted */
-    constexpr int EVERY = 4;                     /* groups between ring upkeeps */
-    constexpr int GWORDS = BITS == 8 ? 6 : 12;   /* ring words one group can consume */
-    constexpr int AHEAD = RWORDS / 4 - 2;        /* chunks kept requested beyond the one being read */
-    constexpr int NTW = (2 << U) / 8;            /* 32 bit words of a 4 bit per entry switch table */
-    static_assert(4 * (AHEAD - 1) >= 2 * EVERY * GWORDS + 4, "ring too small for two upkeep intervals");
-
-    extern __shared__ __align__(16) uint8_t smem_cta[];
-    const uint32_t lane = threadIdx.x & 31, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), bands = a.bands;
-    if (wid * 32 >= a.ntiles) return; /* warps are on their own: no CTA wide barrier anywhere in this kernel */
-    uint8_t *smem = smem_cta + (threadIdx.x >> 5) * plan.warp_smem;
-    const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
-    uint8_t *rb = smem + 32 * LSTRIDE * 4;                          /* [band][lane] running rung */
-    uint32_t *pcf = reinterpret_cast<uint32_t *>(rb + 32 * bands);  /* [band][lane] last common factor */
-    uint8_t *cbs = reinterpret_cast<uint8_t *>(pcf + 32 * bands);   /* [band][lane] band map, header parsing only */
-
-    /* rung switch decode (QB3decode.h:98-116) as two 4 bit per entry tables in registers: length, delta */
-    uint32_t tlen[NTW], tdel[NTW];
-#pragma unroll
-    for (int w = 0; w < NTW; w++) {
-        tlen[w] = tdel[w] = 0;
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const uint32_t d = ds_entry(U, 8 * w + e);
-            tlen[w] |= (d >> 12) << (4 * e);
-            tdel[w] |= (d & 15) << (4 * e);
-        }
-    }
-
-    const uint32_t tile = wid * 32 + lane;
-    const bool live = tile < a.ntiles;
-    const uint8_t *stream = nullptr;
-    uint64_t slen = 0;
-    StreamInfo info;
-    info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
-    if (live) {
-        stream = a.streams + a.offsets[tile];
-        slen = a.lens[tile];
-        parse_header(stream, slen, a, info, cbs + lane, 32);
-    }
-    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
-    const bool go = live && !info.bad && info.mode != M_STORED && !rle;
-    if (live && ch.first) a.status[tile] = go ? ST_SCANNING : info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
-
-    /* the payload as 16 byte chunks from an aligned base; bytes past the end read as zero (bitstream.h:43-49) */
-    const uint8_t *payload = go ? stream + info.data_off : nullptr;
-    const uint64_t plen = go ? slen - info.data_off : 0;
-    const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
-    const uint8_t *abase = go ? payload - mis : a.streams;
-    const uint32_t span = go ? (uint32_t)(mis + plen) : 0; /* the two pass path is only taken for streams far below 4 GB */
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem) + lane * LSTRIDE * 4;
-    /* where this chunk picks the stream up: the reader's registers and the bands' state as the chunk before left them */
-    uint32_t *st = sstate + (size_t)(live ? tile : 0) * (8 + 2 * bands);
-    const bool resume = !ch.first && go;
-    ScanBits<RWORDS> s;
-    s.k = resume ? st[5] : 0;
-    uint32_t issued = s.k >> 2; /* chunks requested so far */
-    auto request = [&]() {
-        const uint32_t start = 16 * issued;
-        const uint32_t nbytes = start >= span ? 0u : min(16u, span - start);
-        cp_async16_zfill(ring_addr + (start & (4 * RWORDS - 1)), abase + (nbytes ? start : 0), nbytes);
-        issued++;
-    };
-    for (int i = 0; i < AHEAD; i++) request();
-    cp_async_commit();
-    cp_async_wait<0>();
-    for (uint32_t c = 0; c < bands; c++) {
-        rb[c * 32 + lane] = resume ? (uint8_t)st[8 + c] : (uint8_t)0;
-        pcf[c * 32 + lane] = resume ? st[8 + bands + c] : 0u;
-    }
-    __syncwarp();
-
-    bool failed = false;
-    if (resume) {
-        s.w0 = mis >> 2; s.sh = 8 * (mis & 3);
-        s.lo = st[0]; s.mid = st[1]; s.hi = st[2];
-        s.nb = st[3]; s.nxt = st[4];
-        failed = st[6] != 0;
-    }
-    else s.open(ring, mis);
-    const bool ftl = info.mode == M_FTL;
-    uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
-
-    const uint32_t per_row = ((a.w + 3) / 4) * bands;
-    uint32_t c = 0, upkeep = 1;
-    const uint32_t g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
-    for (uint32_t g = g_begin; g < g_end; g++) {
-        /* ring upkeep every few groups: request chunks up to AHEAD beyond the one being read. What was requested one
-           upkeep ago has had EVERY groups to land and is waited for; the new requests are for reads two upkeeps away. */
-        if (--upkeep == 0) {
-            upkeep = EVERY;
-            const uint32_t want = (s.k >> 2) + AHEAD;
-            while (__any_sync(0xffffffffu, issued < want)) {
-                if (issued < want) request();
-            }
-            cp_async_commit();
-            cp_async_wait<1>();
-        }
-
-        const uint32_t oldrung = rb[c * 32 + lane];
-        const uint32_t pos = s.consumed();
-        s.refill(ring);
-        const uint32_t x = s.lo;
-        const uint32_t idx = (x >> 1) & LMASK;
-        uint32_t wl = tlen[0], wd = tdel[0];
-#pragma unroll
-        for (int w = 1; w < NTW; w++) if ((idx >> 3) == (uint32_t)w) { wl = tlen[w]; wd = tdel[w]; }
-        const uint32_t sft = 4 * (idx & 7);
-        const uint32_t swl = (x & 1) ? (wl >> sft) & 15 : 1, delta = (x & 1) ? (wd >> sft) & 15 : 0;
-        uint32_t r;
-        if (ftl || delta != 0 || swl == 1) {
-            r = (oldrung + delta) & UMASK;
-            /* rung 0: the flag and its sixteen raw bits go with the switch (QB3decode.h:148-160), and the sixteen
-               steps below run with every length forced to zero, so that all lanes walk the same code */
-            const uint32_t y = x >> swl;
-            s.advance(swl + (r ? 0u : ((y & 1) ? 17u : 1u)));
-            /* a code's length from its two low bits, x0 -> r, 01 -> r + 1, 11 -> r + 2 (QB3decode.h:119-129), as a
-               byte table in a register read with one permute; all zero at rung 0 */
-            const uint32_t lens = r ? 0x02000100u + r * 0x01010101u : 0u;
-            if (BITS == 16 && r == 15) { /* two 17 bit codes exceed what one refill promises; rare */
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    s.refill(ring);
-                    s.advance(__byte_perm(lens, 0u, (s.lo & 3) | 0x4440));
-                }
-            }
-            else {
-#pragma unroll
-                for (int i0 = 0; i0 < 16; i0 += VPR) {
-                    s.refill(ring);
-                    uint32_t used = 0;
-#pragma unroll
-                    for (int i = i0; i < i0 + VPR && i < 16; i++) {
-                        /* selector nibbles 1..3 are zero, so bytes 1..3 of len repeat the table's first byte: junk that
-                           the wrap mode shifts ignore and that cannot carry down into the sum's low byte */
-                        const uint32_t len = __byte_perm(lens, 0u, s.lo & 3);
-                        s.shift(len);
-                        used += len;
-                    }
-                    s.nb -= used & 0xff;
-                }
-            }
-        }
-        else { /* common factor or index group: parsed in full, it is rare */
-            s.advance(swl);
-            W sg[16];
-            uint8_t rbv = (uint8_t)oldrung;
-            W pc = pcf[c * 32 + lane];
-            ScanBitsRef<RWORDS> t; /* a copy: the reader itself must never have its address taken, it lives in registers */
-            t.b = s; t.ring = ring;
-            failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
-            s = t.b;
-            pcf[c * 32 + lane] = pc;
-            r = rbv;
-        }
-        rb[c * 32 + lane] = (uint8_t)r;
-        if (go) rec[g] = (pos << 4) | r;
-        c = c + 1 == bands ? 0 : c + 1;
-    }
-    cp_async_wait<0>();
-    if (go && ch.last) {
-        const uint64_t total = 8 * plen, used = s.consumed();
-        const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
-        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : ST_PARSED;
-    }
-    else if (go) {
-        st[0] = s.lo; st[1] = s.mid; st[2] = s.hi; st[3] = s.nb; st[4] = s.nxt; st[5] = s.k; st[6] = failed;
-        for (uint32_t c2 = 0; c2 < bands; c2++) { st[8 + c2] = rb[c2 * 32 + lane]; st[8 + bands + c2] = pcf[c2 * 32 + lane]; }
-    }
 }
 
 /* Position based reader over a lane's ring, for the 32 and 64 bit scan: codes there can be 65 bits, so nothing is
@@ -1527,6 +903,8 @@ rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_
     else if (tid == 0 && tile_state == ST_PARSED) a.status[tile] = QB3CU_TILE_OK;
 }
 
+#include "qb3_decode_fused.cuh"
+
 template <typename T>
 __global__ void __launch_bounds__(32, 1) parse_kernel(const DecArgs a, const bool only_deferred)
 {
@@ -1685,51 +1063,6 @@ __global__ void __launch_bounds__(256) seal_kernel(uint32_t *status, uint32_t nt
 
 /* ------------------------------------------------------------------ launch */
 
-static int walk_lanes_override()
-{
-    static const int v = [] { const char *e = getenv("QB3CU_LPS"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
-template <typename T, int LPS>
-static cudaError_t launch_walk(const DecArgs &a, uint32_t stage_blocks, uint32_t stage_off, uint32_t sstride, cudaStream_t st)
-{
-    constexpr uint32_t NS = 32 / LPS;
-    const size_t smem = 64 + (size_t)NS * sstride;
-    cudaError_t err = cudaFuncSetAttribute(walk_kernel<T, LPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    walk_kernel<T, LPS><<<(a.ntiles + NS - 1) / NS, 32, smem, st>>>(a, stage_blocks, stage_off, sstride);
-    return cudaGetLastError();
-}
-
-static int decode_path_override() /* QB3CU_DECODE=walk forces the single kernel path */
-{
-    static const int v = [] { const char *e = getenv("QB3CU_DECODE"); return e && e[0] == 'w' ? 1 : 0; }();
-    return v;
-}
-
-template <typename T> static cudaError_t launch_walk_any(const DecArgs &a, cudaStream_t st)
-{
-    /* lanes per stream: the fewer streams there are, the more lanes each one can have for its parallel part */
-    int lps = walk_lanes_override();
-    if (lps != 4 && lps != 8 && lps != 16) lps = a.ntiles >= 2048 ? 8 : 16;
-    const uint32_t hw_bytes = 2 * 16 * (uint32_t)lps;
-    /* staged run of blocks: a multiple of four (rows stay 16 byte multiples) within 8 KB per stream, aiming at 2 KB */
-    const uint32_t block_bytes = 16 * a.bands * (uint32_t)sizeof(T);
-    uint32_t stage_blocks = 0;
-    if (4 * block_bytes <= 8192) {
-        stage_blocks = 4 * (2048 / (4 * block_bytes));
-        if (stage_blocks < 4) stage_blocks = 4;
-        const uint32_t nbx = (a.w + 3) / 4;
-        if (stage_blocks > ((nbx + 3) & ~3u)) stage_blocks = (nbx + 3) & ~3u;
-    }
-    const uint32_t stage_off = (hw_bytes + a.bands * 12 + 15) & ~15u;
-    const uint32_t sstride = stage_off + stage_blocks * block_bytes + 16; /* the spare vector shifts the streams' banks */
-    return lps == 4 ? launch_walk<T, 4>(a, stage_blocks, stage_off, sstride, st)
-         : lps == 8 ? launch_walk<T, 8>(a, stage_blocks, stage_off, sstride, st)
-                    : launch_walk<T, 16>(a, stage_blocks, stage_off, sstride, st);
-}
-
 /*
  * Scratch memory of the two pass decode comes from a stream ordered pool of our own, one per device:
  *  - it keeps what it has been given (the default is to hand freed memory back to the driver at every
@@ -1872,8 +1205,7 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         static const size_t pad = [] { const char *e = getenv("QB3CU_RB_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
         if (pad > smem2) smem2 = pad;
     }
-    if constexpr (NARROW) err = cudaFuncSetAttribute(scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
-    else err = cudaFuncSetAttribute(scan_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+    err = cudaFuncSetAttribute(scan_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     if (err == cudaSuccess) err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
 
     /* With SMs of their own the scans go to our high priority stream and the rebuilds stay on the caller's. Without,
@@ -1917,11 +1249,8 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
         ch.by1 = bounds[i + 1];
         ch.first = i == 0;
         ch.last = i + 1 == nchunks;
-        if constexpr (NARROW)
-            scan_kernel<T><<<scan_ctas, 32 * wpc, scan_smem, sst>>>(a, recs, ngroups, ch, static_cast<uint32_t *>(sstate), plan);
-        else
-            scan_wide_kernel<T><<<scan_ctas, 32 * wpc, scan_smem, sst>>>(a, recs, ngroups, ch,
-                                                                         static_cast<unsigned long long *>(sstate), plan);
+        scan_wide_kernel<T><<<scan_ctas, 32 * wpc, scan_smem, sst>>>(a, recs, ngroups, ch,
+                                                                     static_cast<unsigned long long *>(sstate), plan);
         err = cudaGetLastError();
         if (err == cudaSuccess && nchunks > 1) err = order_after(rst, sst);
         if (err != cudaSuccess) break;
@@ -2025,6 +1354,65 @@ __global__ void __launch_bounds__(128) derle_kernel(const DecArgs a, uint8_t *xb
     }
 }
 
+/*
+ * decode_kernel's launch geometry. Streams per CTA: the batch spread over the SMs (a stream costs its scanner lane the
+ * same time whether the warp holds one stream or 32, so few streams are spread thin and many are packed); units of
+ * about 128 groups in whole rebuild iterations; three unit slots between the scanner and the rebuild warps.
+ */
+template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStream_t st, uint32_t &launches)
+{
+    constexpr uint32_t RWORDS = FUSE_RWORDS(8 * sizeof(T));
+    int dev = 0, nsm = 0, smem_max = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const uint32_t bands = a.bands, nbx = (a.w + 3) / 4;
+    FusePlan pl = {};
+    pl.rwarps = 11;
+    pl.nu = 3;
+    pl.sel_or = 0x4440;
+    pl.bpi = bands <= 32 ? 32 / bands : 1;
+    pl.gpi = bands <= 32 ? pl.bpi * bands : 32;
+    auto whole = [&](uint32_t ub) { return bands <= 32 ? (ub + pl.bpi - 1) / pl.bpi * pl.bpi : ub; };
+    uint32_t ub = 128 / bands;
+    if (ub < 1) ub = 1;
+    ub = whole(ub);
+    if (ub > nbx) ub = nbx;
+    pl.upr = (nbx + ub - 1) / ub;
+    pl.ub = whole((nbx + pl.upr - 1) / pl.upr); /* the block row cut evenly */
+    if (pl.ub > nbx) pl.ub = nbx;
+    pl.upr = (nbx + pl.ub - 1) / pl.ub;
+    pl.rec_stride = (2 + pl.ub * bands) | 1; /* odd: the scanner's lanes write one record each, a stride apart */
+    pl.rowpitch = (pl.ub * 4 * bands * (uint32_t)sizeof(T) + 15) & ~15u;
+    auto layout = [&](uint32_t spc) -> size_t {
+        auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+        size_t off = up((size_t)32 * (RWORDS + 4) * 4);
+        pl.off_band = (uint32_t)off; off = up(off + (size_t)32 * bands * 5);
+        pl.off_rec = (uint32_t)off;  off = up(off + (size_t)pl.nu * (spc + 1) * pl.rec_stride * 4);
+        pl.off_info = (uint32_t)off; off = up(off + (size_t)spc * sizeof(FuseStream));
+        pl.off_cb = (uint32_t)off;   off = up(off + (size_t)spc * bands);
+        pl.off_carry = (uint32_t)off; off = up(off + (size_t)2 * spc * bands * 4);
+        pl.off_stage = (uint32_t)off; off = up(off + (size_t)pl.rwarps * 4 * pl.rowpitch);
+        pl.off_tbl = (uint32_t)off;  off = up(off + 1024 + 2048 + 2 * 64 + 64);
+        pl.off_bar = (uint32_t)off;  off = up(off + (size_t)2 * pl.nu * 8);
+        return off;
+    };
+    uint32_t spc = (a.ntiles + (uint32_t)nsm - 1) / (uint32_t)nsm;
+    if (spc > 32) spc = 32;
+    if (spc < 1) spc = 1;
+    size_t smem = layout(spc);
+    while (smem > (size_t)smem_max && spc > 1) smem = layout(--spc);
+    if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
+    pl.spc = spc;
+    err = allow_max_smem<decode_kernel<T>>();
+    if (err != cudaSuccess) return err;
+    decode_kernel<T><<<(a.ntiles + spc - 1) / spc, 32 * (1 + pl.rwarps), smem, st>>>(a, pl);
+    launches += 1;
+    return cudaGetLastError();
+}
+
+
 /* kernels launched, for the bookkeeping of qb3cu_kernel_launches */
 template <typename T> static cudaError_t launch_decode_t(const DecArgs &a0, cudaStream_t st, uint32_t &launches)
 {
@@ -2055,24 +1443,23 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a0, cuda
         ~FreeLater() { if (p) cudaFreeAsync(p, st); }
     } free_later = {xscratch, st};
     if (a.w >= 4 && a.h >= 4) {
-        /* two passes when a group's start bit fits its record (28 bits, 26 for the wide types); else the single
-           kernel for 8 / 16 bit types and the general path for the others */
-        const uint64_t max_bits = 8 * (1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) + 1));
-        const uint32_t pos_bits = sizeof(T) <= 2 ? 28 : 26;
-        if (max_bits < (1ull << pos_bits) && !decode_path_override()) {
-            err = launch_scan_rebuild<T>(a, st, launches);
+        if constexpr (sizeof(T) <= 2) { /* one fused kernel: a scanner warp and rebuild warps per CTA */
+            err = launch_fused<T>(a, st, launches);
             if (err != cudaSuccess) return err;
             walked = true;
         }
-        else if constexpr (sizeof(T) <= 2) {
-            err = launch_walk_any<T>(a, st);
-            launches += 1;
-            if (err != cudaSuccess) return err;
-            walked = true;
+        else {
+            /* two passes when a group's start bit fits its record (26 bits); else the general path */
+            const uint64_t max_bits = 8 * (1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) + 1));
+            if (max_bits < (1ull << 26)) {
+                err = launch_scan_rebuild<T>(a, st, launches);
+                if (err != cudaSuccess) return err;
+                walked = true;
+            }
         }
     }
     const size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
-    err = cudaFuncSetAttribute(parse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    err = allow_max_smem<parse_kernel<T>>();
     if (err != cudaSuccess) return err;
     parse_kernel<T><<<(a.ntiles + 31) / 32, 32, smem, st>>>(a, walked);
     err = cudaGetLastError();

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "qb3_codes.h"
 #include "../../include/qb3cu.h"
 
@@ -134,6 +136,29 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
     __syncthreads();
     total = scratch[32];
     return scratch[warp] + inc - v;
+}
+
+/*
+ * cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, process wide: it is raised once per kernel and
+ * device to everything the device allows, never per call (two host threads launching the same kernel with different
+ * sizes would otherwise race between setting it and launching).
+ */
+template <auto Kernel> static cudaError_t allow_max_smem()
+{
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return cudaSuccess;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, Kernel);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
 }
 
 } // namespace qb3

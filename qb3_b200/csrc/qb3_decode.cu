@@ -1369,7 +1369,8 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const uint32_t bands = a.bands, nbx = (a.w + 3) / 4;
     FusePlan pl = {};
-    pl.rwarps = 11;
+    pl.nwarps = 12; /* the scanner, two warps that leave its scheduler alone, nine that rebuild */
+    pl.rwarps = 9;
     pl.nu = 3;
     pl.sel_or = 0x4440;
     pl.bpi = bands <= 32 ? 32 / bands : 1;
@@ -1407,7 +1408,7 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     pl.spc = spc;
     err = allow_max_smem<decode_kernel<T>>();
     if (err != cudaSuccess) return err;
-    decode_kernel<T><<<(a.ntiles + spc - 1) / spc, 32 * (1 + pl.rwarps), smem, st>>>(a, pl);
+    decode_kernel<T><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
     launches += 1;
     return cudaGetLastError();
 }

@@ -28,6 +28,7 @@
 
 struct FusePlan {
     uint32_t spc, rwarps;     /* streams per CTA (1..32), rebuild warps */
+    uint32_t nwarps;          /* warps in the CTA: the scanner is the last, those on its scheduler idle */
     uint32_t ub, upr, nu;     /* blocks per unit, units per block row, unit slots */
     uint32_t rec_stride;      /* words per (slot, stream): two anchor words, then a record per group */
     uint32_t rowpitch;        /* bytes between the staged rows of a rebuild warp */
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
 
     /* scanner state that the header gives; parsed by the scanner's lanes, shared with the rebuild through infos */
     const uint32_t tile = blockIdx.x * spc + lane;
-    const bool scanner = warp == pl.rwarps; /* the last warp: the scheduler's arbiter prefers the highest warp id */
+    const bool scanner = warp == pl.nwarps - 1; /* the last warp: the scheduler's arbiter prefers the highest warp id */
     const bool live = scanner && lane < spc && tile < a.ntiles;
     bool go = false, ftl_l = false;
     uint32_t mis = 0, span = 0;
@@ -242,16 +243,16 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
         const uint8_t *rsrc = abase;
         uint32_t rdst = 0, issued = 0;
         int32_t rleft = (int32_t)span;
-        auto request = [&]() {
+        auto request = [&](bool on) {
             const uint32_t nbytes = (uint32_t)min(max(rleft, 0), 16);
-            cp_async16_zfill(ring_addr + rdst, rsrc, nbytes);
-            if (rdst == 0) cp_async16_zfill(ring_addr + 4 * RWORDS, rsrc, nbytes); /* the mirror of the first four words */
-            if (rleft > 16) rsrc += 16; /* never points past the stream's last chunk */
-            rleft -= 16;
-            rdst = (rdst + 16) & (4 * RWORDS - 1);
-            issued++;
+            if (on) cp_async16_zfill(ring_addr + rdst, rsrc, nbytes);
+            if (on && rdst == 0) cp_async16_zfill(ring_addr + 4 * RWORDS, rsrc, nbytes); /* the mirror of the first four words */
+            if (on && rleft > 16) rsrc += 16; /* never points past the stream's last chunk */
+            rleft -= on ? 16 : 0;
+            rdst = (rdst + (on ? 16u : 0u)) & (4 * RWORDS - 1);
+            issued += on ? 1u : 0u;
         };
-        for (int i = 0; i < AHEAD; i++) request();
+        for (int i = 0; i < AHEAD; i++) request(true);
         cp_async_commit();
         cp_async_wait<0>();
         for (uint32_t c = 0; c < bands; c++) { rbs[c * 32 + lane] = 0; pcfs[c * 32 + lane] = 0; }
@@ -291,102 +292,116 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
         uint32_t c = 0;
         const uint32_t csb_sa = tbl_sa + 2048 + 2 * (2u << U);
         const uint32_t rlane = lane < spc ? lane : spc; /* lanes without a stream write their records to a spare row */
-        for (uint32_t u = 0; u < nunits; u++) {
-            const uint32_t slot = u % pl.nu, j = u % pl.upr;
-            const uint32_t b0 = j * pl.ub, ng = min(pl.ub, nbx - b0) * bands;
-            if (u >= pl.nu) mbar_wait(bar_sa + 8 * (pl.nu + slot), ((u / pl.nu) - 1) & 1);
-            uint32_t *rp = recs + (size_t)(slot * (spc + 1) + rlane) * pl.rec_stride;
-            abs_bits += (uint32_t)(pos - apos);
-            apos = pos;
-            rp[0] = (uint32_t)abs_bits;
-            rp[1] = (uint32_t)(abs_bits >> 32);
-            rp += 2;
-            for (uint32_t g0 = 0; g0 < ng; g0 += EVERY) {
-                /* ring upkeep every EVERY groups: request chunks up to AHEAD beyond the one being read; of the copy
-                   groups in flight all but the latest PENDING are waited for */
-                {
-                    const uint32_t want = (pos >> 7) + 1 + AHEAD;
-                    while (__any_sync(0xffffffffu, issued < want)) {
-                        if (issued < want) request();
-                    }
-                    cp_async_commit();
-                    cp_async_wait<PENDING>();
-                }
-                const uint32_t gn = min((uint32_t)EVERY, ng - g0);
-#pragma unroll 1
-                for (uint32_t gi = 0; gi < gn; gi++) {
-                    const uint32_t oldrung = rbs[c * 32 + lane];
-                    const uint32_t gpos = pos;
-                    const uint32_t e = lds_u8(csb_sa + (z & ((4u << U) - 1)));
-                    const uint32_t swl = e >> 4, delta = e & 15;
-                    /* a signal (a change flag with delta 0, QB3decode.h:619) opens a common factor or index group: the
-                       walk below then runs on meaningless lengths, harmlessly, and the group is parsed again after it */
-                    const bool special = !ftl_l && delta == 0 && swl != 1;
-                    uint32_t r = (oldrung + delta) & UMASK;
-                    /* Lengths by the code's two low bits, x0 -> r, 01 -> r + 1, 11 -> r + 2 (QB3decode.h:119-129). At rung 0
-                       all sixteen are zero, so that every lane walks the same code, and the group's flag with its sixteen
-                       raw bits (QB3decode.h:148-160) goes as the first value's length: 1 or 17 by the flag. Products, not
-                       selects: a predicate takes three times as long to arrive as a register. */
-                    const uint32_t nz = min(r, 1u);
-                    const uint32_t lens = nz * (0x02000100u + r * 0x01010101u);
-                    const uint32_t lens_first = (nz ^ 1) * 0x11011101u + lens;
+        /* RARE: with the groups that are parsed again after the walk -- common factor and index groups, and the 16 bit
+           groups at rung 15. A batch of FTL streams of 8 bit data has neither, and the loop without the check saves
+           a branch with its reconvergence point per group. */
+        uint32_t e_next = lds_u8(csb_sa + (z & ((4u << U) - 1))), rung_next = 0;
+        auto walk = [&](auto rare_tag) {
+            constexpr bool RARE = decltype(rare_tag)::value;
+            for (uint32_t u = 0; u < nunits; u++) {
+                const uint32_t slot = u % pl.nu, j = u % pl.upr;
+                const uint32_t b0 = j * pl.ub, ng = min(pl.ub, nbx - b0) * bands;
+                if (u >= pl.nu) mbar_wait(bar_sa + 8 * (pl.nu + slot), ((u / pl.nu) - 1) & 1);
+                uint32_t *rp = recs + (size_t)(slot * (spc + 1) + rlane) * pl.rec_stride;
+                abs_bits += (uint32_t)(pos - apos);
+                apos = pos;
+                rp[0] = (uint32_t)abs_bits;
+                rp[1] = (uint32_t)(abs_bits >> 32);
+                rp += 2;
+                for (uint32_t g0 = 0; g0 < ng; g0 += EVERY) {
+                    /* ring upkeep every EVERY groups: request chunks up to AHEAD beyond the one being read; of the copy
+                       groups in flight all but the latest PENDING are waited for */
                     {
-                        const uint32_t zs = z, zhs = zh;
-                        uint32_t before = swl, len;
-                        z >>= swl;
-#pragma unroll
-                        for (int i = 0; i < NV0; i++) {
-                            len = code_len(i ? lens : lens_first, z);
-                            if (i + 1 < NV0) { z >>= len; before += len; }
-                        }
-                        next_window(zs, zhs, before, len);
-#pragma unroll
-                        for (int i0 = NV0; i0 < 16; i0 += VPB) {
-                            const uint32_t zs2 = z, zhs2 = zh;
-                            before = 0;
-#pragma unroll
-                            for (int i = i0; i < i0 + VPB && i < 16; i++) {
-                                len = code_len(lens, z);
-                                if (i + 1 < i0 + VPB && i + 1 < 16) { z >>= len; before += len; }
+                        const uint32_t want = (pos >> 7) + 1 + AHEAD;
+                        /* as many rounds as the lane that is furthest behind needs, the same for every lane: one reduction, no
+                           vote and no divergent branch per request */
+                        const uint32_t rounds = __reduce_max_sync(0xffffffffu, want - issued);
+    #pragma unroll 1
+                        for (uint32_t q = 0; q < rounds; q++) request(issued < want);
+                        cp_async_commit();
+                        cp_async_wait<PENDING>();
+                    }
+                    const uint32_t gn = min((uint32_t)EVERY, ng - g0);
+    #pragma unroll 1
+                    for (uint32_t gi = 0; gi < gn; gi++) {
+                        const uint32_t oldrung = rung_next, e = e_next;
+                        const uint32_t gpos = pos;
+                        const uint32_t swl = e >> 4, delta = e & 15;
+                        /* a signal (a change flag with delta 0, QB3decode.h:619) opens a common factor or index group: the
+                           walk below then runs on meaningless lengths, harmlessly, and the group is parsed again after it */
+                        const bool special = RARE && !ftl_l && delta == 0 && swl != 1;
+                        uint32_t r = (oldrung + delta) & UMASK;
+                        /* Lengths by the code's two low bits, x0 -> r, 01 -> r + 1, 11 -> r + 2 (QB3decode.h:119-129). At rung 0
+                           all sixteen are zero, so that every lane walks the same code, and the group's flag with its sixteen
+                           raw bits (QB3decode.h:148-160) goes as the first value's length: 1 or 17 by the flag. Products, not
+                           selects: a predicate takes three times as long to arrive as a register. */
+                        const uint32_t nz = min(r, 1u);
+                        const uint32_t lens = nz * (0x02000100u + r * 0x01010101u);
+                        const uint32_t lens_first = (nz ^ 1) * 0x11011101u + lens;
+                        {
+                            const uint32_t zs = z, zhs = zh;
+                            uint32_t before = swl, len;
+                            z >>= swl;
+    #pragma unroll
+                            for (int i = 0; i < NV0; i++) {
+                                len = code_len(i ? lens : lens_first, z);
+                                if (i + 1 < NV0) { z >>= len; before += len; }
                             }
-                            next_window(zs2, zhs2, before, len);
+                            next_window(zs, zhs, before, len);
+    #pragma unroll
+                            for (int i0 = NV0; i0 < 16; i0 += VPB) {
+                                const uint32_t zs2 = z, zhs2 = zh;
+                                before = 0;
+    #pragma unroll
+                                for (int i = i0; i < i0 + VPB && i < 16; i++) {
+                                    len = code_len(lens, z);
+                                    if (i + 1 < i0 + VPB && i + 1 < 16) { z >>= len; before += len; }
+                                }
+                                next_window(zs2, zhs2, before, len);
+                            }
                         }
+                        auto reopen = [&](uint32_t at) { /* the reader afresh at a ring position */
+                            pos = at;
+                            const uint32_t wi = at >> 5;
+                            wa = ring[(wi + 1) & (RWORDS - 1)]; wb = ring[(wi + 2) & (RWORDS - 1)]; wc = ring[(wi + 3) & (RWORDS - 1)];
+                            z = __funnelshift_r(ring[wi & (RWORDS - 1)], wa, at);
+                            zh = __funnelshift_r(wa, wb, at);
+                        };
+                        if (RARE && BITS == 16 && r == 15 && !special) {
+                            /* two 17 bit codes do not fit a window, so the walk above may have gone wrong: again, a value at a
+                               time; rare */
+                            reopen(gpos);
+                            next_window(z, zh, 0, swl);
+    #pragma unroll 1
+                            for (int i = 0; i < 16; i++) next_window(z, zh, 0, code_len(lens, z));
+                        }
+                        if (special) { /* common factor or index group: parsed in full from the ring, it is rare */
+                            RingBits<RWORDS> t;
+                            t.ring = ring;
+                            t.pos = gpos + swl;
+                            W sg[16];
+                            uint8_t rbv = (uint8_t)oldrung;
+                            W pc = pcfs[c * 32 + lane];
+                            failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
+                            pcfs[c * 32 + lane] = pc;
+                            r = rbv;
+                            reopen(t.pos);
+                        }
+                        rbs[c * 32 + lane] = (uint8_t)r;
+                        c = c + 1 == bands ? 0 : c + 1;
+                        /* the next group's switch entry and old rung are asked for now: their latency passes behind the
+                           stores and the loop's end instead of ahead of the next group's first instruction */
+                        e_next = lds_u8(csb_sa + (z & ((4u << U) - 1)));
+                        rung_next = rbs[c * 32 + lane];
+                        rp[g0 + gi] = ((gpos - apos) << 4) | oldrung;
                     }
-                    auto reopen = [&](uint32_t at) { /* the reader afresh at a ring position */
-                        pos = at;
-                        const uint32_t wi = at >> 5;
-                        wa = ring[(wi + 1) & (RWORDS - 1)]; wb = ring[(wi + 2) & (RWORDS - 1)]; wc = ring[(wi + 3) & (RWORDS - 1)];
-                        z = __funnelshift_r(ring[wi & (RWORDS - 1)], wa, at);
-                        zh = __funnelshift_r(wa, wb, at);
-                    };
-                    if (BITS == 16 && r == 15 && !special) {
-                        /* two 17 bit codes do not fit a window, so the walk above may have gone wrong: again, a value at a
-                           time; rare */
-                        reopen(gpos);
-                        next_window(z, zh, 0, swl);
-#pragma unroll 1
-                        for (int i = 0; i < 16; i++) next_window(z, zh, 0, code_len(lens, z));
-                    }
-                    if (special) { /* common factor or index group: parsed in full from the ring, it is rare */
-                        RingBits<RWORDS> t;
-                        t.ring = ring;
-                        t.pos = gpos + swl;
-                        W sg[16];
-                        uint8_t rbv = (uint8_t)oldrung;
-                        W pc = pcfs[c * 32 + lane];
-                        failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
-                        pcfs[c * 32 + lane] = pc;
-                        r = rbv;
-                        reopen(t.pos);
-                    }
-                    rbs[c * 32 + lane] = (uint8_t)r;
-                    rp[g0 + gi] = ((gpos - apos) << 4) | oldrung;
-                    c = c + 1 == bands ? 0 : c + 1;
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_sa + 8 * slot);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_sa + 8 * slot);
-        }
+        };
+        if (BITS == 16 || __any_sync(0xffffffffu, go && !ftl_l)) walk(std::true_type());
+        else walk(std::false_type());
         cp_async_wait<0>();
         if (go) {
             const uint64_t total = 8 * plen, used = (uint32_t)(pos - 8 * mis);
@@ -397,7 +412,11 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
     }
 
     /* ==================================================================== rebuild warps */
-    const uint32_t rw = warp, FULL = 0xffffffffu;
+    /* The scanner keeps its warp scheduler to itself: the warps that would share it (same warp id modulo 4) leave, the
+       others are numbered 0 .. rwarps - 1. Whatever a rebuild warp issues there is taken from the one warp the whole
+       CTA waits for. */
+    if ((warp & 3) == (pl.nwarps - 1 & 3)) return;
+    const uint32_t rw = warp - (warp >> 2) - ((warp & 3) > (pl.nwarps - 1 & 3) ? 1 : 0), FULL = 0xffffffffu;
     const uint32_t rowpitch = pl.rowpitch, rowelems = rowpitch / (uint32_t)sizeof(T);
     uint8_t *stage = smem + pl.off_stage + (size_t)rw * 4 * rowpitch;
     const bool small_bands = bands <= 32;

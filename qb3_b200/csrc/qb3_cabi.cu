@@ -174,6 +174,13 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     a.segs = (a.nbx + a.seg_blocks - 1) / a.seg_blocks;
     uint32_t threads = (a.seg_blocks * a.bands + 31) & ~31u;
     if (threads > 512) return QB3CU_ERR_PARAM;
+    /* bulk copies (TMA) for the row staging when every segment's rows are whole 16 byte units at 16 byte addresses */
+    a.bulk_stage = a.vec_stage && (((uintptr_t)d_src | src_tile_pitch | (a.stride * tsize)) & 15) == 0;
+    for (uint32_t sg = 0; sg < a.segs && a.bulk_stage; sg++) {
+        const uint32_t bx0 = sg * a.seg_blocks, nblk = a.seg_blocks < a.nbx - bx0 ? a.seg_blocks : a.nbx - bx0;
+        const uint32_t xs = 4 * bx0 < a.vw - 4 ? 4 * bx0 : a.vw - 4, xe = 4 * (bx0 + nblk) < a.vw ? 4 * (bx0 + nblk) : a.vw;
+        if (((xs * a.bands * tsize) | ((xe - xs) * a.bands * tsize)) & 15) a.bulk_stage = 0;
+    }
     a.rowpitch = ((a.seg_blocks * 4 * a.bands * tsize + 15) & ~15u) + 16;
     a.win_words = ((a.hdr_len * 8 + 128 + threads * max_group_bits(bits)) / 32 + 16 + 3) & ~3u;
     size_t smem = (size_t)a.win_words * 4 + 8 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4

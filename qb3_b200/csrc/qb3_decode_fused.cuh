@@ -61,7 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) break;
-        __nanosleep(400); /* a waiting warp must not take issue slots from the scanner */
+        __nanosleep(1000); /* a waiting warp must not take issue slots from the scanner */
     }
 }
 __device__ __forceinline__ int32_t lds_s8(uint32_t addr)

@@ -116,6 +116,32 @@ __device__ __forceinline__ void stage_rows(const EncArgs &a, const uint8_t *src,
     }
 }
 
+/*
+ * Bulk copy engine (TMA, one dimension): one thread moves a whole row global -> shared with a single instruction
+ * (cp.async.bulk, SASS UBLKCP) and an mbarrier counts the bytes in. Source, destination and size are multiples of 16.
+ */
+__device__ __forceinline__ void bulk_row(uint32_t smem_dst, const void *gmem_src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 /* ------------------------------------------------------------------ bit packing */
 
 /* Per thread writer into the shared 32 bit word window. The thread owns bits [s, e). */
@@ -556,11 +582,35 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     const uint32_t blk = tid / a.bands, c = tid - blk * a.bands; /* this thread's block in the segment and band */
     const uint32_t stage_bytes = 4 * a.rowpitch;
     /* segment (by, sg) -> staged rows; issued one segment ahead */
+    /* Rows that are whole 16 byte units at 16 byte addresses (a.bulk_stage, decided by the host for the launch) travel
+       by the bulk copy engine: thread 0 issues four copies per segment and an mbarrier per staging buffer counts the
+       bytes in -- no per thread address arithmetic, no issue slots (it was a sixth of the kernel's instructions as
+       16 byte cp.async). Anything else goes through stage_rows. */
+    __shared__ __align__(8) unsigned long long stage_bar[2];
+    const uint32_t bar_sa = (uint32_t)__cvta_generic_to_shared(stage_bar);
+    if (a.bulk_stage && tid == 0) {
+        mbar_init(bar_sa, 1);
+        mbar_init(bar_sa + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     auto issue = [&](uint32_t by, uint32_t sg, uint32_t buf) {
         const uint32_t bx0 = sg * a.seg_blocks, nblk = min(a.seg_blocks, a.nbx - bx0);
         const uint32_t xs = min(4 * bx0, a.vw - 4), xe = min(4 * (bx0 + nblk), a.vw);
+        if (a.bulk_stage) {
+            if (tid == 0) {
+                const uint32_t rowbytes = (xe - xs) * a.bands * (uint32_t)sizeof(T);
+                const uint64_t lpitch = a.stride * sizeof(T);
+                const uint8_t *g0 = src + ((uint64_t)min(4 * by, a.vh - 4) * a.stride + (uint64_t)xs * a.bands) * sizeof(T);
+                const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(stage + buf * stage_bytes);
+                mbar_expect(bar_sa + 8 * buf, 4 * rowbytes);
+#pragma unroll
+                for (int r = 0; r < 4; r++) bulk_row(d0 + r * a.rowpitch, g0 + r * lpitch, rowbytes, bar_sa + 8 * buf);
+            }
+            return;
+        }
         stage_rows<T>(a, src, stage + buf * stage_bytes, min(4 * by, a.vh - 4), xs, xe - xs);
     };
+    if (a.bulk_stage) __syncthreads(); /* the barriers exist before anybody waits on them */
     if (a.small != 3) issue(by_lo, 0, 0);
     cp_async_commit();
 
@@ -576,6 +626,7 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
                 if (nby < by_hi) issue(nby, nsg, par ^ 1);
                 cp_async_commit();
                 cp_async_wait<1>();
+                if (a.bulk_stage) mbar_wait(bar_sa + 8 * par, (it >> 1) & 1);
             }
             __syncthreads(); /* also orders the header / carry / table writes before their first use */
             const uint8_t *sbuf = stage + par * stage_bytes;

@@ -533,6 +533,7 @@ int main(int argc, char **argv)
 {
     Options opt;
     if (!parse_args(argc, argv, opt)) return usage(opt);
+    qb3cu_api_max_bands(QB3_MAXBANDS); /* this tool is compiled with -DQB3_MAXBANDS=256: its band maps hold that many */
     if (opt.info) return info_file(opt.in_fname);
     if (opt.is_folder) return opt.decode ? decode_folder(opt) : encode_folder(opt);
     if (opt.decode) return decode_file(opt, opt.in_fname, out_name(opt, opt.in_fname, opt.raw_spec.empty() ? ".pnm" : ".raw"));

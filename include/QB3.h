@@ -31,12 +31,14 @@ extern "C" {
 #endif
 
 /*
- * Upper limit on the band count; sizes the band-map arrays callers pass to
- * qb3_set_encoder_coreband / qb3_get_coreband. The reference ships 16 and
- * allows up to 256 (QB3.h:33-34); this library is built for 256.
+ * Upper limit on the band count; sizes the band-map arrays callers pass to qb3_set_encoder_coreband /
+ * qb3_get_coreband. 16 as in the reference (QB3.h:33-34, which allows "up to 256"): qb3_create_encoder and
+ * qb3_read_start refuse more bands than that, exactly like the reference library, so that a caller built with
+ * size_t bandmap[16] is never handed more. A program that wants more compiles with -DQB3_MAXBANDS=n (n <= 256,
+ * the kernels' own limit) and tells the library once, before its first handle: qb3cu_api_max_bands(n) in qb3cu.h.
  */
 #if !defined(QB3_MAXBANDS)
-#define QB3_MAXBANDS 256
+#define QB3_MAXBANDS 16
 #endif
 
 /* opaque handles (reference: QB3.h:36-37) */

@@ -160,6 +160,11 @@ LIBQB3_EXPORT int qb3cu_pipe_decode(qb3cu_pipe *pipe, const void *h_streams, con
 LIBQB3_EXPORT void *qb3cu_host_alloc(size_t bytes);
 LIBQB3_EXPORT void qb3cu_host_free(void *p);
 
+/* Band limit of the QB3.h functions (qb3_create_encoder, qb3_read_start): 16 when the library is loaded, like the
+   reference's QB3_MAXBANDS (QB3.h:34); a caller compiled with a larger QB3_MAXBANDS raises it here, up to
+   QB3CU_MAXBANDS. Returns the limit now in force. The batched entry points above always take up to QB3CU_MAXBANDS. */
+LIBQB3_EXPORT uint32_t qb3cu_api_max_bands(uint32_t bands);
+
 /* cudaError_t of the most recent failing CUDA call made by this library on the calling thread. */
 LIBQB3_EXPORT int qb3cu_last_cuda_error(void);
 

@@ -698,10 +698,20 @@ size_t qb3o_encode(qb3o_enc *e, const void *src, void *destination)
                 img[pix * nb + c] = v;
             }
         }
+    /* Quantised images and images with a side under 4 are coded through a copy of the control structure
+       (encs subimg(*p), QB3encode.cpp:405; smallimg, :352): the running state is read, never written back. */
+    uint64_t (*st)[QB3O_MAXBANDS] = NULL;
+    uint64_t *prev = e->prev, *runbits = e->runbits, *cf = e->cf;
+    if (e->quanta >= 2 || w < 4 || h < 4) {
+        st = malloc(3 * sizeof(*st));
+        memcpy(st[0], e->prev, sizeof(*st)); memcpy(st[1], e->runbits, sizeof(*st)); memcpy(st[2], e->cf, sizeof(*st));
+        prev = st[0]; runbits = st[1]; cf = st[2];
+    }
     stream_cfg k = {vw, vh, nb, e->cband, e->order ? e->order : HILBERT, bits,
-                    mode != MODE_FTL, mode == 1 || mode == 5, e->prev, e->runbits, e->cf};
+                    mode != MODE_FTL, mode == 1 || mode == 5, prev, runbits, cf};
     encode_stream(img, &k, &s);
     free(img);
+    free(st);
 
     size_t len = (s.pos + 7) / 8;
     s.pos = len * 8;

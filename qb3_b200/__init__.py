@@ -26,6 +26,15 @@ class Config(C.Structure):
 
 
 _lib = None
+_testing = None
+
+
+def testing_lib():
+    """libqb3cu_testing.so: the closed forms and the header writer as host functions, for the CPU-only tests."""
+    global _testing
+    if _testing is None:
+        _testing = C.CDLL(os.path.join(_HERE, "libqb3cu_testing.so"))
+    return _testing
 
 
 def lib():

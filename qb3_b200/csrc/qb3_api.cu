@@ -5,6 +5,7 @@
  * bits are only ever touched by the CUDA kernels. Without a usable CUDA device qb3_encode and
  * qb3_read_data fail (return 0, encoder state QB3E_LIBERR): there is no CPU codec here.
  */
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -59,19 +60,35 @@ struct decs {
     DevBuf src, dst, aux;
 };
 
+/* QB3_REF_COMPAT=1, read once when it is first needed */
+static int ref_compat_env()
+{
+    static const int v = [] { const char *e = getenv("QB3_REF_COMPAT"); return e && e[0] == '1' ? 1 : 0; }();
+    return v;
+}
+
 static bool ensure_stream(cudaStream_t &s)
 {
     if (s) return true;
     return note_cuda(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) == QB3CU_OK;
 }
 
+/* what QB3_MAXBANDS is for the callers of the QB3.h functions: the reference's 16 unless a caller says otherwise */
+static std::atomic<uint32_t> g_api_max_bands(16);
+
 extern "C" {
+
+uint32_t qb3cu_api_max_bands(uint32_t bands)
+{
+    if (bands >= 1 && bands <= QB3CU_MAXBANDS) g_api_max_bands = bands;
+    return g_api_max_bands;
+}
 
 /* ------------------------------------------------------------------ encoder */
 
 encsp qb3_create_encoder(size_t w, size_t h, size_t b, qb3_dtype dt)
 {
-    if (w == 0 || w > 0x10000 || h == 0 || h > 0x10000 || b == 0 || b > QB3CU_MAXBANDS || (unsigned)dt > QB3_I64)
+    if (w == 0 || w > 0x10000 || h == 0 || h > 0x10000 || b == 0 || b > g_api_max_bands || (unsigned)dt > QB3_I64)
         return nullptr;
     encsp p = new encs();
     if (qb3cu_config_init(&p->cfg, (uint32_t)w, (uint32_t)h, (uint32_t)b, (uint32_t)dt) != QB3CU_OK) {
@@ -164,11 +181,16 @@ size_t qb3_encode(encsp p, void *source, void *destination)
     uint64_t *d_state = d_size + 2;
     cudaStream_t st = p->stream;
     uint64_t size = 0;
+    const bool keep_state = c.quanta > 1 || c.width < 4 || c.height < 4;
     bool ok = note_cuda(cudaMemcpy2DAsync(p->src.p, line, source, pitch, line, c.height, cudaMemcpyHostToDevice, st)) == QB3CU_OK
         && note_cuda(cudaMemcpyAsync(d_state, p->state, nstate * 8, cudaMemcpyHostToDevice, st)) == QB3CU_OK
         && qb3cu_encode_batch(&dc, p->src.p, line * c.height, p->dst.p, slot, d_size, d_status, d_state, 1, st) == QB3CU_OK
         && note_cuda(cudaMemcpyAsync(&size, d_size, 8, cudaMemcpyDeviceToHost, st)) == QB3CU_OK
-        && note_cuda(cudaMemcpyAsync(p->state, d_state, nstate * 8, cudaMemcpyDeviceToHost, st)) == QB3CU_OK
+        /* The running state comes back into the handle for plain images only. Quantised images and images with a side
+           under 4 are coded through a copy of the handle in the reference (encs subimg(*p), QB3encode.cpp:405, and
+           smallimg, :352), so there the handle's own state stays as it was and a second qb3_encode gives the same
+           stream again. */
+        && (keep_state || note_cuda(cudaMemcpyAsync(p->state, d_state, nstate * 8, cudaMemcpyDeviceToHost, st)) == QB3CU_OK)
         && note_cuda(cudaStreamSynchronize(st)) == QB3CU_OK;
     if (ok && size > 0 && size <= slot)
         ok = note_cuda(cudaMemcpy(destination, p->dst.p, size, cudaMemcpyDeviceToHost)) == QB3CU_OK;
@@ -206,7 +228,7 @@ decsp qb3_read_start(void *source, size_t source_size, size_t *image_size)
     p->nbands = 1 + s[8];
     p->type = s[9];
     p->mode = s[10];
-    if (p->nbands > QB3CU_MAXBANDS || (p->mode >= QB3M_END && p->mode != QB3M_STORED)
+    if (p->nbands > g_api_max_bands || (p->mode >= QB3M_END && p->mode != QB3M_STORED)
         || ((s[11] | s[12]) & 0x80) || p->type > QB3_I64) {
         delete p;
         return nullptr;
@@ -221,8 +243,7 @@ decsp qb3_read_start(void *source, size_t source_size, size_t *image_size)
     if (p->mode <= QB3M_CF_RLE) p->order = ZCURVE;
     /* band map when no CB chunk follows: identity, which is what the format says (doc/QB3.md:255). The reference
        leaves it zeroed; QB3_REF_COMPAT=1 in the environment selects that behaviour. */
-    const char *compat = getenv("QB3_REF_COMPAT");
-    if (!(compat && compat[0] == '1'))
+    if (!ref_compat_env())
         for (size_t c = 0; c < p->nbands; c++) p->cband[c] = (uint8_t)c;
     p->error = QB3E_OK;
     p->stage = 1;
@@ -320,8 +341,7 @@ size_t qb3_read_data(decsp p, void *destination)
     const size_t ts = TSIZE[p->type], line = p->xsize * p->nbands * ts, out = line * p->ysize;
     const size_t pitch = (p->stride ? p->stride : p->xsize * p->nbands) * ts;
     if (pitch < line) { p->error = QB3E_EINV; return 0; }
-    const char *compat = getenv("QB3_REF_COMPAT");
-    const int ref_compat = compat && compat[0] == '1';
+    const int ref_compat = ref_compat_env();
     if (!ensure_stream(p->stream) || !p->src.reserve(p->s_total + 16) || !p->dst.reserve(out) || !p->aux.reserve(32)) {
         p->error = QB3E_LIBERR;
         return 0;

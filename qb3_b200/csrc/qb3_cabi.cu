@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "qb3_device.cuh"
+#include "qb3_host.h"
 
 namespace qb3 {
 cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st);
@@ -19,12 +20,6 @@ typedef void (*rows_ready_fn)(void *ctx, uint32_t row0, uint32_t row1, cudaStrea
 int decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
                       void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream,
                       uint32_t row_chunks, rows_ready_fn rows_ready, void *rows_ctx);
-
-/* The host pipeline and the two pass decode keep many CUDA streams busy at once; with the driver's default of 8
-   hardware queues, streams share queues and wait for each other (measured: 2 x slower pipelines). The variable is read
-   when the CUDA context is created, so this only helps when the library is loaded before that -- otherwise set it in
-   the environment. An existing setting is left alone. */
-static const int g_env_once = [] { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); return 0; }();
 
 static thread_local int g_last_cuda_error = 0;
 static std::atomic<uint64_t> g_launches(0);
@@ -47,38 +42,6 @@ static bool geometry_ok(const qb3cu_config *c)
         && c->bands >= 1 && c->bands <= QB3CU_MAXBANDS && c->dtype <= 7;
 }
 
-/* Header bytes up to and including "DT" (reference: QB3encode.cpp:189-268, doc/QB3.md:228-259) */
-static uint32_t build_headers(const qb3cu_config *c, uint32_t mode_byte, uint64_t order, uint8_t *out)
-{
-    uint32_t n = 0;
-    auto put = [&](uint64_t v, uint32_t bytes) { for (uint32_t i = 0; i < bytes; i++) out[n++] = (uint8_t)(v >> (8 * i)); };
-    put(0x80334251u, 4); /* "QB3\200" */
-    put(c->width - 1, 2);
-    put(c->height - 1, 2);
-    put(c->bands - 1, 1);
-    put(c->dtype, 1);
-    put(mode_byte, 1);
-    bool banddiff = false;
-    for (uint32_t b = 0; b < c->bands; b++) banddiff |= c->cband[b] != b;
-    if (mode_byte != M_STORED && banddiff) {
-        put('C' | ('B' << 8), 2);
-        put(c->bands, 2);
-        for (uint32_t b = 0; b < c->bands; b++) put(c->cband[b], 1);
-    }
-    if (c->quanta >= 2) {
-        const uint32_t qbytes = 1 + topbit64(c->quanta) / 8;
-        put('Q' | ('V' << 8), 2);
-        put(qbytes, 2);
-        put(c->quanta, qbytes);
-    }
-    if (order != ZCURVE && mode_byte != M_STORED) {
-        put('S' | ('C' << 8), 2);
-        put(8, 2);
-        put(order, 8);
-    }
-    put('D' | ('T' << 8), 2);
-    return n;
-}
 } // namespace qb3
 
 using namespace qb3;
@@ -201,7 +164,7 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     const bool best = a.mode == M_CF_Z || a.mode == M_CF_H;
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (!best && a.small == 0 && a.nby >= 16 && ntiles < (size_t)4 * nsm && !getenv("QB3CU_ENC_ONE_CTA")) {
+    if (!best && a.small == 0 && a.nby >= 16 && ntiles < (size_t)4 * nsm) {
         uint32_t parts = (uint32_t)(((size_t)6 * nsm + ntiles - 1) / ntiles); /* a few CTAs per SM to balance the load */
         if (parts > a.nby / 8) parts = a.nby / 8; /* eight block rows to a part at least */
         if (parts > 64) parts = 64;
@@ -291,35 +254,6 @@ int qb3cu_pack_streams(const void *d_slots, size_t slot_bytes, const uint64_t *d
                                   static_cast<cudaStream_t>(stream));
     if (err == cudaSuccess) count_launches(1 + (ntiles + 65534) / 65535);
     return note_cuda(err);
-}
-
-/* ---- host-logic probes for the CPU-only tests: the closed forms the kernels use (qb3_codes.h) ---- */
-
-LIBQB3_EXPORT uint32_t qb3cu_debug_cs_entry(uint32_t U, uint32_t d) { return cs_entry(U, d); }
-LIBQB3_EXPORT uint32_t qb3cu_debug_cs_signal(uint32_t U) { return cs_signal(U); }
-LIBQB3_EXPORT uint32_t qb3cu_debug_ds_entry(uint32_t U, uint32_t x) { return ds_entry(U, x); }
-/* (len << 12) | bits of a stand-alone value at a rung below 11, the reference's CRG table entry */
-LIBQB3_EXPORT uint32_t qb3cu_debug_code(uint32_t rung, uint32_t v, int group)
-{
-    uint64_t lo; uint32_t hi;
-    if (rung == 0) return 0x1000u | (v & 1);
-    if (group ? group_swaps(rung) : single_swaps(rung)) v = mswap<uint32_t>(v, rung);
-    const uint32_t len = code_bits<uint32_t>(v, rung, lo, hi);
-    return (len << 12) | (uint32_t)lo;
-}
-LIBQB3_EXPORT uint32_t qb3cu_debug_decode(uint32_t rung, uint32_t x, int group)
-{
-    uint32_t len;
-    if (rung == 0) return 0x1000u | (x & 1);
-    uint32_t v = (uint32_t)decode_bits(x, 0, rung, len);
-    if (group ? group_swaps(rung) : single_swaps(rung)) v = mswap<uint32_t>(v, rung);
-    return (len << 12) | v;
-}
-LIBQB3_EXPORT int qb3cu_debug_step(uint32_t M, int decode) { return decode ? step_decode_index(M) : step_encode_index(M); }
-LIBQB3_EXPORT uint32_t qb3cu_debug_headers(const qb3cu_config *cfg, uint32_t mode_byte, uint8_t *out)
-{
-    const uint64_t order = cfg->order ? cfg->order : (cfg->mode <= 3 ? ZCURVE : HILBERT);
-    return build_headers(cfg, mode_byte, order, out);
 }
 
 } /* extern "C" */

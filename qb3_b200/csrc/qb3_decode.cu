@@ -1125,12 +1125,6 @@ static cudaStream_t aux_stream(cudaStream_t user, bool high)
     return free_slot->aux;
 }
 
-static int decode_chunks_override() /* QB3CU_CHUNKS=n: row chunks of the two pass decode, 1 = no pipelining */
-{
-    static const int v = [] { const char *e = getenv("QB3CU_CHUNKS"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
 /*
  * scan_kernel + rebuild_kernel, pipelined: the tile batch is cut into chunks of block rows, scan runs chunk after
  * chunk on the caller's stream and hands its reader state on through memory, and the rebuild of a chunk starts on a
@@ -1143,8 +1137,7 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     constexpr bool NARROW = sizeof(T) <= 2;
     typedef typename traits<T>::W W;
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
-    uint32_t nchunks = decode_chunks_override() > 0 ? (uint32_t)decode_chunks_override() : a.row_chunks ? a.row_chunks
-                                                                                    : a.rows_ready ? 16 : 12;
+    uint32_t nchunks = a.row_chunks ? a.row_chunks : a.rows_ready ? 16 : 12;
     if (nchunks > 64) nchunks = 64;
     if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* four block rows per chunk on average, at least */
     /*
@@ -1180,9 +1173,9 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     /* four warps to an SM only for 8 bit data: with the longer rings of the other types that many copies in flight per
        SM slow each other down (measured: 16 bit scans take 1.8 times as long four to an SM) */
-    uint32_t wpc = getenv("QB3CU_SCAN_WPC") ? (uint32_t)atoi(getenv("QB3CU_SCAN_WPC")) : sizeof(T) == 1 ? 4 : 1;
+    uint32_t wpc = 1;
     while (wpc > 1 && wpc * smem1 > (size_t)smem_max) wpc >>= 1;
-    const bool own_sm = nchunks > 1 && !a.shared_sm && (int)((nwarps + wpc - 1) / wpc) * 3 <= nsm && !getenv("QB3CU_SCAN_SHARED_SM");
+    const bool own_sm = nchunks > 1 && !a.shared_sm && (int)((nwarps + wpc - 1) / wpc) * 3 <= nsm;
     if (!own_sm) wpc = 1;
     cudaStream_t aux = nchunks > 1 ? aux_stream(st, own_sm) : nullptr;
     if (nchunks > 1 && !aux) { cudaFreeAsync(scratch, st); return cudaErrorUnknown; }
@@ -1201,12 +1194,8 @@ template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, c
     const uint32_t threads = (seg_blocks * a.bands + 31) & ~31u;
     const uint32_t rowpitch = (seg_blocks * 4 * a.bands * (uint32_t)sizeof(T) + 15) & ~15u;
     size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * (sizeof(W) + 1) + (size_t)a.bands * (2 * sizeof(W) + 1) + 16;
-    {   /* experiment knob: QB3CU_RB_SMEM=bytes pads rebuild_kernel's shared memory to lower its occupancy */
-        static const size_t pad = [] { const char *e = getenv("QB3CU_RB_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
-        if (pad > smem2) smem2 = pad;
-    }
-    err = cudaFuncSetAttribute(scan_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(rebuild_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    err = allow_max_smem<scan_wide_kernel<T>>();
+    if (err == cudaSuccess) err = allow_max_smem<rebuild_kernel<T>>();
 
     /* With SMs of their own the scans go to our high priority stream and the rebuilds stay on the caller's. Without,
        the scans stay on the caller's stream, back to back, and the rebuilds go to the second stream: a scan launched

@@ -8,6 +8,8 @@
 #include <stdint.h>
 
 #include <mutex>
+#include <set>
+#include <utility>
 
 #include "qb3_codes.h"
 #include "../../include/qb3cu.h"
@@ -144,23 +146,23 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
  * device to everything the device allows, never per call (two host threads launching the same kernel with different
  * sizes would otherwise race between setting it and launching).
  */
-template <auto Kernel> static cudaError_t allow_max_smem()
+inline cudaError_t allow_max_smem_of(const void *kernel)
 {
     static std::mutex mu;
-    static bool done[64] = {};
+    static std::set<std::pair<int, const void *>> done;
     int dev = 0, optin = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     std::lock_guard<std::mutex> lock(mu);
-    if (done[dev]) return cudaSuccess;
+    if (done.count(std::make_pair(dev, kernel))) return cudaSuccess;
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, Kernel);
+    e = cudaFuncGetAttributes(&fa, kernel);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
-    if (e == cudaSuccess) done[dev] = true;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) done.insert(std::make_pair(dev, kernel));
     return e;
 }
+template <auto Kernel> static cudaError_t allow_max_smem() { return allow_max_smem_of(reinterpret_cast<const void *>(Kernel)); }
 
 } // namespace qb3
 #endif

@@ -1268,12 +1268,12 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
     auto kern = best ? (curve == 1 ? encode_kernel<T, true, 1> : curve == 2 ? encode_kernel<T, true, 2> : encode_kernel<T, true, 0>)
                      : (curve == 1 ? encode_kernel<T, false, 1> : curve == 2 ? encode_kernel<T, false, 2> : encode_kernel<T, false, 0>);
     if constexpr (sizeof(T) == 1) {
-        if (!best && curve == 1 && threads <= 384 && !getenv("QB3CU_ENC_SPARSE")) kern = encode_kernel<T, false, 1, true>;
+        if (!best && curve == 1 && threads <= 384) kern = encode_kernel<T, false, 1, true>;
     }
     if constexpr (sizeof(T) <= 2) { /* BEST: two CTAs to an SM (85 registers) hide the wait for the threads with index groups */
-        if (best && curve == 1 && threads <= 384 && !getenv("QB3CU_ENC_SPARSE")) kern = encode_kernel<T, true, 1, true>;
+        if (best && curve == 1 && threads <= 384) kern = encode_kernel<T, true, 1, true>;
     }
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = allow_max_smem_of(reinterpret_cast<const void *>(kern));
     if (err != cudaSuccess) return err;
     kern<<<(unsigned)(ntiles * (a.parts > 1 ? a.parts : 1)), threads, smem, st>>>(a);
     err = cudaGetLastError();

@@ -35,6 +35,9 @@ class QB3Lib:
     def __init__(self, path, maxbands):
         self.lib = L = C.CDLL(path)
         self.maxbands = maxbands
+        if hasattr(L, "qb3cu_api_max_bands"):  # the product: 16 bands like the reference until a caller asks for more
+            L.qb3cu_api_max_bands.restype, L.qb3cu_api_max_bands.argtypes = C.c_uint32, [C.c_uint32]
+            L.qb3cu_api_max_bands(maxbands)
         vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
         sig = {
             "qb3_create_encoder": (vp, [sz, sz, sz, C.c_int]),
@@ -201,7 +204,7 @@ class Oracle:
             f.restype, f.argtypes = C.c_uint16, [C.c_uint, C.c_uint]
         L.qb3o_signal.restype, L.qb3o_signal.argtypes = C.c_uint16, [C.c_uint]
 
-    def encode(self, img, mode=MODE_FTL, cband=None, quanta=1, away=False, stride=None, reps=1):
+    def encode(self, img, mode=MODE_FTL, cband=None, quanta=1, away=False, stride=None, reps=1, order=None):
         img = np.ascontiguousarray(img)
         h, w, b = img.shape
         e = _OEnc()
@@ -213,6 +216,8 @@ class Oracle:
                 raise ValueError("coreband")
         e.quanta, e.away = quanta, int(away)
         self.lib.qb3o_set_mode(C.byref(e), mode)
+        if order is not None:  # an arbitrary 4x4 scan curve, written as an "SC" chunk (QB3encode.cpp:246-252)
+            e.order = order
         if stride is not None:
             e.stride = stride
         cap = self.lib.qb3o_max_encoded_size(C.byref(e))

@@ -111,6 +111,15 @@ def test_api_quanta_stride_state():
     # running state persists across qb3_encode calls on one handle
     img = content("synth", 16, 16, 1, np.uint8)
     assert P.encode(img, mode=MODE_BASE, reps=2) == O.encode(img, mode=MODE_BASE, reps=2)
+    # ... but not for quantised images or images with a side under 4: the reference codes those through a copy of the
+    # handle (QB3encode.cpp:405, :352), so the second stream equals the first and decodes
+    for kw in (dict(mode=MODE_BASE, quanta=3), dict(mode=MODE_BEST, quanta=5)):
+        a = P.encode(img, reps=2, **kw)
+        assert a == O.encode(img, reps=2, **kw) and a[0] == a[1]
+    small = content("synth", 3, 40, 2, np.uint16)
+    a = P.encode(small, mode=MODE_BASE, reps=2)
+    assert a == O.encode(small, mode=MODE_BASE, reps=2) and a[0] == a[1]
+    assert np.array_equal(P.decode(a[1]), small)
 
 
 def test_api_small_and_many_bands():
@@ -567,3 +576,29 @@ def test_many_caller_streams():
     pipe.decode(packed, off, sz, n, back, stat)
     assert not stat.any() and np.array_equal(back, tiles)
     pipe.close()
+
+
+def test_arbitrary_scan_curves():
+    """Streams whose "SC" chunk names a curve that is neither Hilbert nor Z (QB3decode.cpp:231-250) decode on every
+    path -- the QB3.h wrapper, the batch entry point -- and the batch encoder writes them when asked to (cfg.order)."""
+    P, O = product(), oracle()
+    for order in (0x0123456789abcdef, 0xfedcba9876543210, 0x048c159d26ae37bf, 0x5a0f3c96e17d48b2):
+        for (w, h, b, dt, mode, cb) in ((16, 12, 1, np.uint8, MODE_FTL, None), (64, 40, 3, np.uint8, MODE_BASE, None),
+                                       (21, 9, 3, np.uint16, MODE_BASE, None), (12, 8, 2, np.int32, MODE_BEST, [0, 0]),
+                                       (20, 16, 1, np.uint64, MODE_FTL, None)):
+            n = 5
+            tiles = np.stack([content("synth", w, h, b, dt, seed=t) for t in range(n)])
+            want = [O.encode(tiles[t], mode=mode, order=order, cband=cb) for t in range(n)]
+            assert np.array_equal(P.decode(want[0]), tiles[0])
+            torch = torch_mod()
+            cfg = q.config(w, h, b, dtype_code(dt), mode=mode, cband=cb)
+            cfg.order = order
+            src = torch.from_numpy(tiles.view(np.uint8).reshape(n, -1)).cuda()
+            dst, sizes, status = q.encode_batch(cfg, src, n)
+            offsets = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+            out, st = q.decode_batch(cfg, dst, offsets, sizes, n)
+            torch.cuda.synchronize()
+            assert not status.cpu().numpy().any() and not st.cpu().numpy().any()
+            sizes_h, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
+            assert [dst_h[t, :sizes_h[t]].tobytes() for t in range(n)] == want
+            assert np.array_equal(out.cpu().numpy().view(tiles.dtype).reshape(tiles.shape), tiles)

@@ -35,8 +35,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), n
 
 
+def test_no_test_probes_in_the_product_library():
+    assert not [n for n in os.popen("nm -D --defined-only " + PRODUCT_SO).read().split() if "debug" in n]
+
+
 def test_closed_form_tables_equal_oracle_tables():
-    L, O = q.lib(), oracle().lib
+    L, O = q.testing_lib(), oracle().lib
     for f in (L.qb3cu_debug_cs_entry, L.qb3cu_debug_ds_entry, L.qb3cu_debug_code, L.qb3cu_debug_decode, L.qb3cu_debug_cs_signal):
         f.restype = C.c_uint32
     for U in (3, 4, 5, 6):
@@ -58,7 +62,7 @@ def test_closed_form_tables_equal_oracle_tables():
 
 
 def test_step_rule():
-    L = q.lib()
+    L = q.testing_lib()
     for M in range(1, 1 << 16, 97):
         n = bin(M).count("1")
         is_step = (M & (M + 1)) == 0
@@ -68,7 +72,7 @@ def test_step_rule():
 
 
 def test_header_bytes_match_oracle_streams():
-    L = q.lib()
+    L = q.testing_lib()
     out = (C.c_uint8 * 320)()
     for (w, h, b, dt, kw) in [(8, 8, 1, np.uint8, {}), (17, 9, 3, np.uint16, {}), (12, 8, 5, np.int32, dict(cband=[2, 2, 2, 2, 4])),
                               (9, 7, 1, np.int32, dict(quanta=3)), (8, 8, 2, np.uint64, dict(quanta=70000, mode=MODE_BASE)),
@@ -226,3 +230,29 @@ def test_pipe_needs_a_device_and_valid_arguments():
     assert L.qb3cu_pipe_decode(None, None, None, None, None, 0, None, 0, 0) == 1
     L.qb3cu_pipe_destroy(None)
     L.qb3cu_host_free(None)
+
+
+def test_band_limit_is_the_references_until_a_caller_raises_it():
+    """QB3_MAXBANDS is 16 in the reference's header and library (QB3.h:34, QB3encode.cpp:28-30, QB3decode.cpp:152):
+    the QB3.h functions here refuse a 17th band the same way until qb3cu_api_max_bands() is told otherwise."""
+    L = product().lib
+    assert "#define QB3_MAXBANDS 16" in open(os.path.join(ROOT, "include", "QB3.h")).read()
+    try:
+        assert L.qb3cu_api_max_bands(16) == 16
+        assert not L.qb3_create_encoder(8, 8, 17, 0)
+        e = L.qb3_create_encoder(8, 8, 16, 0)
+        assert e
+        L.qb3_destroy_encoder(e)
+        s17 = np.frombuffer(oracle().encode(content("ramp", 8, 8, 17, np.uint8)), np.uint8).copy()
+        dims = (C.c_size_t * 3)()
+        assert not L.qb3_read_start(s17.ctypes.data, s17.size, dims)
+        assert L.qb3cu_api_max_bands(0) == 16 and L.qb3cu_api_max_bands(257) == 16  # out of range: unchanged
+        assert L.qb3cu_api_max_bands(256) == 256
+        e = L.qb3_create_encoder(8, 8, 17, 0)
+        assert e
+        L.qb3_destroy_encoder(e)
+        d = L.qb3_read_start(s17.ctypes.data, s17.size, dims)
+        assert d and dims[2] == 17
+        L.qb3_destroy_decoder(d)
+    finally:
+        L.qb3cu_api_max_bands(256)

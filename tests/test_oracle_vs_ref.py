@@ -149,9 +149,30 @@ def test_encoder_state_persists_across_calls():
     a = ref().encode(img, mode=MODE_BEST, reps=2)
     b = oracle().encode(img, mode=MODE_BEST, reps=2)
     assert a == b and a[0] != a[1]
+    # ... except for quantised images, which the reference codes through a copy of the handle (QB3encode.cpp:405):
+    # the handle's own state stays put and the second stream equals the first
+    for mode in (MODE_BASE, MODE_BEST):
+        a = ref().encode(img, mode=mode, quanta=3, reps=2)
+        assert a == oracle().encode(img, mode=mode, quanta=3, reps=2) and a[0] == a[1]
 
 
 def test_max_encoded_size():
     for (w, h, b, dt) in [(512, 512, 3, np.uint8), (513, 511, 1, np.int32), (7, 5, 16, np.uint64), (65536, 3, 1, np.uint16)]:
         assert ref().max_encoded_size(w, h, b, dt) == oracle().max_encoded_size(w, h, b, dt)
     assert oracle().max_encoded_size(512, 512, 3, np.uint8) == 891904
+
+
+CURVES = (0x0123456789abcdef, 0xfedcba9876543210, 0x048c159d26ae37bf, 0x5a0f3c96e17d48b2)
+
+
+def test_arbitrary_scan_curve_streams_decode_with_the_reference():
+    """An "SC" chunk may carry any permutation of the sixteen block positions (QB3decode.cpp:231-250). The reference's
+    encoder only ever writes Hilbert, so the oracle writes the streams and the reference's decoder pins them."""
+    for order in CURVES:
+        for (w, h, b, dt, mode) in ((16, 12, 1, np.uint8, MODE_FTL), (21, 9, 3, np.uint16, MODE_BASE), (12, 8, 2, np.int32, MODE_BEST)):
+            img = content("synth", w, h, b, dt)
+            cb = None if b != 2 else [0, 0]
+            s = oracle().encode(img, mode=mode, order=order, cband=cb)
+            assert b"SC\x08\x00" + order.to_bytes(8, "little") in s[:64]
+            assert np.array_equal(ref().decode(s), img)
+            assert np.array_equal(oracle().decode(s), img)

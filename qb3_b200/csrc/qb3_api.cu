@@ -60,11 +60,13 @@ struct decs {
     DevBuf src, dst, aux;
 };
 
-/* QB3_REF_COMPAT=1, read once when it is first needed */
+/* QB3_REF_COMPAT=1 in the environment: a stream without a CB chunk decodes with the reference's all-zero band map
+   (SURVEY 4.3 D1). A user facing switch, looked up when a decoder handle is made so that a program can change it
+   between images; the only environment variable this library reads. */
 static int ref_compat_env()
 {
-    static const int v = [] { const char *e = getenv("QB3_REF_COMPAT"); return e && e[0] == '1' ? 1 : 0; }();
-    return v;
+    const char *e = getenv("QB3_REF_COMPAT");
+    return e && e[0] == '1' ? 1 : 0;
 }
 
 static bool ensure_stream(cudaStream_t &s)

@@ -156,6 +156,30 @@ LIBQB3_EXPORT int qb3cu_pipe_decode(qb3cu_pipe *pipe, const void *h_streams, con
                                     const uint64_t *h_lens, void *h_dst, size_t dst_tile_pitch, uint32_t *h_status,
                                     int ref_compat, size_t ntiles);
 
+/*
+ * ---- Several devices from one process ----
+ *
+ * The same two calls over G devices: the batch is cut into G contiguous tile ranges, range g goes through a pipe on
+ * devices[g] driven by its own host thread, nothing is exchanged between devices (tiles are independent QB3 streams,
+ * SURVEY 8e). devices == NULL: devices 0 .. ndevices - 1; ndevices == 0: every device of the process. A device may
+ * be named more than once (two pipes on it).
+ * qb3cu_multi_encode: range g is packed into its own share of h_packed, the share starting at g * (capacity / G
+ * rounded down to 16): within a range the streams are back to back as for qb3cu_pipe_encode, between ranges there is
+ * a gap; h_offsets[t] / h_sizes[t] say where stream t is, *h_total = bytes of streams written (gaps not counted).
+ * ntiles * qb3cu_slot_bytes() of capacity always suffices. The result feeds qb3cu_multi_decode or qb3cu_pipe_decode.
+ */
+typedef struct qb3cu_multi qb3cu_multi;
+LIBQB3_EXPORT qb3cu_multi *qb3cu_multi_create(const qb3cu_config *cfg, const int *devices, int ndevices,
+                                              size_t chunk_tiles, int depth);
+LIBQB3_EXPORT void qb3cu_multi_destroy(qb3cu_multi *multi);
+LIBQB3_EXPORT int qb3cu_multi_devices(const qb3cu_multi *multi);
+LIBQB3_EXPORT int qb3cu_multi_encode(qb3cu_multi *multi, const void *h_src, size_t src_tile_pitch, void *h_packed,
+                                     size_t packed_capacity, uint64_t *h_offsets, uint64_t *h_sizes, uint64_t *h_total,
+                                     size_t ntiles);
+LIBQB3_EXPORT int qb3cu_multi_decode(qb3cu_multi *multi, const void *h_streams, const uint64_t *h_offsets,
+                                     const uint64_t *h_lens, void *h_dst, size_t dst_tile_pitch, uint32_t *h_status,
+                                     int ref_compat, size_t ntiles);
+
 /* Page locked host memory for the buffers above (cudaHostAlloc / cudaFreeHost). NULL on failure. */
 LIBQB3_EXPORT void *qb3cu_host_alloc(size_t bytes);
 LIBQB3_EXPORT void qb3cu_host_free(void *p);

@@ -62,6 +62,13 @@ def lib():
         L.qb3cu_pipe_encode.argtypes = [vp, vp, sz, vp, sz, u64p, u64p, u64p, sz]
         L.qb3cu_pipe_decode.restype = C.c_int
         L.qb3cu_pipe_decode.argtypes = [vp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz]
+        L.qb3cu_multi_create.restype, L.qb3cu_multi_create.argtypes = vp, [cfgp, C.POINTER(C.c_int), C.c_int, sz, C.c_int]
+        L.qb3cu_multi_destroy.restype, L.qb3cu_multi_destroy.argtypes = None, [vp]
+        L.qb3cu_multi_devices.restype, L.qb3cu_multi_devices.argtypes = C.c_int, [vp]
+        L.qb3cu_multi_encode.restype = C.c_int
+        L.qb3cu_multi_encode.argtypes = [vp, vp, sz, vp, sz, u64p, u64p, u64p, sz]
+        L.qb3cu_multi_decode.restype = C.c_int
+        L.qb3cu_multi_decode.argtypes = [vp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz]
         L.qb3cu_host_alloc.restype, L.qb3cu_host_alloc.argtypes = vp, [sz]
         L.qb3cu_host_free.restype, L.qb3cu_host_free.argtypes = None, [vp]
         L.qb3cu_last_cuda_error.restype, L.qb3cu_last_cuda_error.argtypes = C.c_int, []
@@ -208,6 +215,45 @@ class Pipe:
         rc = lib().qb3cu_pipe_decode(self.handle, self._ptr(packed), self._ptr(offsets), self._ptr(lens), self._ptr(out),
                                      tile_pitch, self._ptr(status), int(ref_compat), ntiles)
         _check(rc, "qb3cu_pipe_decode")
+
+
+class Multi(Pipe):
+    """qb3cu_multi: the same two calls, the batch sharded over several devices from this one process (a host thread
+    and a pipe per device inside the library). devices: list of device indices, None = all."""
+
+    def __init__(self, cfg, devices=None, chunk_tiles=0, depth=0):
+        self.cfg = cfg
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        self.handle = lib().qb3cu_multi_create(C.byref(cfg), arr, len(devices) if devices else 0, chunk_tiles, depth)
+        if not self.handle:
+            raise RuntimeError("qb3cu_multi_create failed: cuda=%d (there is no CPU fallback)" % lib().qb3cu_last_cuda_error())
+        self.ndevices = lib().qb3cu_multi_devices(self.handle)
+
+    def close(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.qb3cu_multi_destroy(h)
+
+    __del__ = close
+
+    def encode(self, src, ntiles, packed, offsets, sizes, tile_pitch=None):
+        ts = TYPESIZE[self.cfg.dtype]
+        if tile_pitch is None:
+            tile_pitch = (self.cfg.stride if self.cfg.stride else self.cfg.width * self.cfg.bands) * self.cfg.height * ts
+        total = C.c_uint64(0)
+        cap = packed.numel() * packed.element_size() if hasattr(packed, "numel") else packed.nbytes
+        rc = lib().qb3cu_multi_encode(self.handle, self._ptr(src), tile_pitch, self._ptr(packed), cap, self._ptr(offsets),
+                                      self._ptr(sizes), C.addressof(total), ntiles)
+        _check(rc, "qb3cu_multi_encode")
+        return total.value
+
+    def decode(self, packed, offsets, lens, ntiles, out, status, tile_pitch=None, ref_compat=False):
+        ts = TYPESIZE[self.cfg.dtype]
+        if tile_pitch is None:
+            tile_pitch = (self.cfg.stride if self.cfg.stride else self.cfg.width * self.cfg.bands) * self.cfg.height * ts
+        rc = lib().qb3cu_multi_decode(self.handle, self._ptr(packed), self._ptr(offsets), self._ptr(lens), self._ptr(out),
+                                      tile_pitch, self._ptr(status), int(ref_compat), ntiles)
+        _check(rc, "qb3cu_multi_decode")
 
 
 def shard_range(ntiles, rank, world):

@@ -1389,6 +1389,9 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
         return off;
     };
     uint32_t spc = (a.ntiles + (uint32_t)nsm - 1) / (uint32_t)nsm;
+    /* Several batches in flight at once (the host pipeline): a batch takes as long on few SMs as on all of them -- its
+       time is one stream's serial parse -- so it is packed onto as few as possible and leaves the rest to the others. */
+    if (a.shared_sm) spc = 32;
     if (spc > 32) spc = 32;
     if (spc < 1) spc = 1;
     size_t smem = layout(spc);

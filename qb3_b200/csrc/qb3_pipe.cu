@@ -359,3 +359,116 @@ int qb3cu_pipe_decode(qb3cu_pipe *p, const void *h_streams, const uint64_t *h_of
 }
 
 } /* extern "C" */
+
+/* ------------------------------------------------------------------ several devices from one process */
+
+/*
+ * qb3cu_multi_*: a batch in host memory sharded over G devices by one call (contiguous tile ranges, one
+ * host thread and one pipe per device, nothing exchanged between devices -- tiles are independent QB3 streams).
+ * What a C++ caller (GDAL / MRF, cqb3cu) needs to use all the GPUs of a box without writing the sharding itself.
+ */
+#include <thread>
+
+struct qb3cu_multi {
+    std::vector<qb3cu_pipe *> pipes; /* pipe g lives on device devs[g] */
+    std::vector<int> devs;
+};
+
+namespace qb3 {
+/* tiles [lo, hi) of n for share g of G: contiguous, sizes differ by at most one */
+static void share_of(size_t n, size_t g, size_t G, size_t &lo, size_t &hi)
+{
+    lo = n * g / G;
+    hi = n * (g + 1) / G;
+}
+} // namespace qb3
+
+extern "C" {
+
+qb3cu_multi *qb3cu_multi_create(const qb3cu_config *cfg, const int *devices, int ndevices, size_t chunk_tiles, int depth)
+{
+    int count = 0;
+    if (!cfg || ndevices < 0 || ndevices > 64 || note_cuda(cudaGetDeviceCount(&count)) != QB3CU_OK || count < 1) return nullptr;
+    if (ndevices == 0) ndevices = count; /* all of them */
+    qb3cu_multi *m = new (std::nothrow) qb3cu_multi;
+    if (!m) return nullptr;
+    int before = 0;
+    cudaGetDevice(&before);
+    for (int g = 0; g < ndevices; g++) {
+        const int dev = devices ? devices[g] : g;
+        qb3cu_pipe *p = nullptr;
+        if (dev >= 0 && dev < count && cudaSetDevice(dev) == cudaSuccess) p = qb3cu_pipe_create(cfg, chunk_tiles, depth);
+        if (!p) {
+            cudaSetDevice(before);
+            qb3cu_multi_destroy(m);
+            return nullptr;
+        }
+        m->pipes.push_back(p);
+        m->devs.push_back(dev);
+    }
+    cudaSetDevice(before);
+    return m;
+}
+
+void qb3cu_multi_destroy(qb3cu_multi *m)
+{
+    if (!m) return;
+    for (qb3cu_pipe *p : m->pipes) qb3cu_pipe_destroy(p);
+    delete m;
+}
+
+int qb3cu_multi_devices(const qb3cu_multi *m) { return m ? (int)m->pipes.size() : 0; }
+
+int qb3cu_multi_encode(qb3cu_multi *m, const void *h_src, size_t src_tile_pitch, void *h_packed, size_t packed_capacity,
+                       uint64_t *h_offsets, uint64_t *h_sizes, uint64_t *h_total, size_t ntiles)
+{
+    if (!m || m->pipes.empty() || !h_src || !h_packed || !h_offsets || !h_sizes || !h_total) return QB3CU_ERR_PARAM;
+    const size_t G = m->pipes.size();
+    /* every device packs its tile range into its own share of h_packed, shares starting at 16 byte multiples */
+    const size_t share = (packed_capacity / G) & ~(size_t)15;
+    std::vector<int> rc(G, QB3CU_OK);
+    std::vector<uint64_t> used(G, 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++)
+        th.emplace_back([&, g] {
+            size_t lo, hi;
+            share_of(ntiles, g, G, lo, hi);
+            if (hi == lo) return;
+            rc[g] = qb3cu_pipe_encode(m->pipes[g], static_cast<const uint8_t *>(h_src) + lo * src_tile_pitch, src_tile_pitch,
+                                      static_cast<uint8_t *>(h_packed) + g * share, share, h_offsets + lo, h_sizes + lo,
+                                      &used[g], hi - lo);
+            for (size_t t = lo; t < hi && rc[g] == QB3CU_OK; t++) h_offsets[t] += g * share;
+        });
+    for (std::thread &t : th) t.join();
+    uint64_t total = 0;
+    for (size_t g = 0; g < G; g++) {
+        if (rc[g] != QB3CU_OK) return rc[g];
+        total += used[g];
+    }
+    *h_total = total;
+    return QB3CU_OK;
+}
+
+int qb3cu_multi_decode(qb3cu_multi *m, const void *h_streams, const uint64_t *h_offsets, const uint64_t *h_lens, void *h_dst,
+                       size_t dst_tile_pitch, uint32_t *h_status, int ref_compat, size_t ntiles)
+{
+    if (!m || m->pipes.empty() || !h_streams || !h_offsets || !h_lens || !h_dst || !h_status) return QB3CU_ERR_PARAM;
+    const size_t G = m->pipes.size();
+    std::vector<int> rc(G, QB3CU_OK);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++)
+        th.emplace_back([&, g] {
+            size_t lo, hi;
+            share_of(ntiles, g, G, lo, hi);
+            if (hi == lo) return;
+            rc[g] = qb3cu_pipe_decode(m->pipes[g], h_streams, h_offsets + lo, h_lens + lo,
+                                      static_cast<uint8_t *>(h_dst) + lo * dst_tile_pitch, dst_tile_pitch, h_status + lo,
+                                      ref_compat, hi - lo);
+        });
+    for (std::thread &t : th) t.join();
+    for (size_t g = 0; g < G; g++)
+        if (rc[g] != QB3CU_OK) return rc[g];
+    return QB3CU_OK;
+}
+
+} /* extern "C" */

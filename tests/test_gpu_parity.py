@@ -602,3 +602,26 @@ def test_arbitrary_scan_curves():
             sizes_h, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
             assert [dst_h[t, :sizes_h[t]].tobytes() for t in range(n)] == want
             assert np.array_equal(out.cpu().numpy().view(tiles.dtype).reshape(tiles.shape), tiles)
+
+
+def test_multi_device_entry_point():
+    """qb3cu_multi_*: one call shards a host batch over several devices (here every device of the box, and -- so that
+    the sharding runs on a single GPU box too -- device 0 named three times). Streams equal the oracle's, tile by tile,
+    whatever the sharding; decode gives the tiles back."""
+    torch = torch_mod()
+    w, h, b, n = 96, 64, 3, 37
+    tiles = synth_tiles(n, w, h, b, np.uint8)
+    want = [oracle().encode(tiles[t], mode=MODE_BASE) for t in range(n)]
+    cfg = q.config(w, h, b, 0, mode=MODE_BASE)
+    for devices in (None, [0, 0, 0], [0]):
+        m = q.Multi(cfg, devices, chunk_tiles=5, depth=2)
+        assert m.ndevices == (torch.cuda.device_count() if devices is None else len(devices))
+        packed = np.zeros(n * q.slot_bytes(cfg), np.uint8)
+        offs, sizes = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        total = m.encode(tiles, n, packed, offs, sizes)
+        assert total == sum((len(s) + 15) // 16 * 16 for s in want)
+        assert [packed[int(o):int(o + l)].tobytes() for o, l in zip(offs, sizes)] == want
+        out, status = np.zeros_like(tiles), np.ones(n, np.uint32)
+        m.decode(packed, offs, sizes, n, out, status)
+        assert not status.any() and np.array_equal(out, tiles)
+        m.close()

@@ -144,6 +144,7 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
         const uint32_t xs = 4 * bx0 < a.vw - 4 ? 4 * bx0 : a.vw - 4, xe = 4 * (bx0 + nblk) < a.vw ? 4 * (bx0 + nblk) : a.vw;
         if (((xs * a.bands * tsize) | ((xe - xs) * a.bands * tsize)) & 15) a.bulk_stage = 0;
     }
+    a.simd8 = a.bulk_stage && tsize == 1 && a.bands <= 4 && a.vw % 4 == 0 && (a.order == HILBERT || a.order == ZCURVE);
     a.rowpitch = ((a.seg_blocks * 4 * a.bands * tsize + 15) & ~15u) + 16;
     a.win_words = ((a.hdr_len * 8 + 128 + threads * max_group_bits(bits)) / 32 + 16 + 3) & ~3u;
     size_t smem = (size_t)a.win_words * 4 + 8 * (size_t)a.rowpitch + 2 * (size_t)a.bands * 8 + 36 * 4

@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
     constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1, TM = (1u << BITS) - 1;
     constexpr int RWORDS = FUSE_RWORDS(BITS);    /* ring words per lane */
     constexpr int LSTRIDE = RWORDS + 4;          /* words between the rings of two lanes: banks shifted; the four spare
-                                                    words mirror the ring's first four, so that a read of up to three
-                                                    words from any ring position never has to wrap */
+                                                    words mirror the ring's first four, so that a read of up to four
+                                                    words on from any ring position never has to wrap */
     constexpr int EVERY = 8;                     /* groups between ring upkeeps */
     constexpr int GWORDS = BITS == 8 ? 7 : 12;   /* ring words one group of any kind can consume */
     constexpr int AHEAD = RWORDS / 4 - 2;        /* chunks kept requested beyond the one being read */
@@ -239,6 +239,10 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
         /* ================================================================ scanner */
         const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
         const uint32_t ring_addr = smem_sa + lane * LSTRIDE * 4;
+        /* the band count in a register of its own: read from the constant bank in the loop, its latency is on every
+           group's path (the compiler prefers to reload it) */
+        uint32_t nbands;
+        asm volatile("mov.u32 %0, %1;" : "=r"(nbands) : "r"(bands));
         /* ring fill state: the next chunk's source, its place in the ring, the bytes of the stream left from there */
         const uint8_t *rsrc = abase;
         uint32_t rdst = 0, issued = 0;
@@ -255,19 +259,19 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
         for (int i = 0; i < AHEAD; i++) request(true);
         cp_async_commit();
         cp_async_wait<0>();
-        for (uint32_t c = 0; c < bands; c++) { rbs[c * 32 + lane] = 0; pcfs[c * 32 + lane] = 0; }
+        for (uint32_t cc = 0; cc < bands; cc++) { rbs[cc * 32 + lane] = 0; pcfs[cc * 32 + lane] = 0; }
         __syncwarp();
 
         /*
          * The reader. z holds the 32 stream bits from bit pos on, zh the 32 after them; wa, wb are the ring words that
-         * follow the one holding bit pos, wc the one after those (fetched ahead). Within a window of values only z moves
+         * follow the one holding bit pos, wc and wd the two after those (fetched ahead). Within a window of values only z moves
          * (plain right shifts: the parse chain is AND, permute, shift per value and nothing else); the window's last
          * shift is a funnel shift from a copy of (z, zh) moved along beside the chain, which lands on the next window's
          * z directly. The next zh is then cut afresh from the raw words -- off the chain, it is first needed a window
          * later.
          */
         uint32_t pos = 8 * mis;
-        uint32_t wa = ring[(mis >> 2) + 1], wb = ring[(mis >> 2) + 2], wc = ring[(mis >> 2) + 3];
+        uint32_t wa = ring[(mis >> 2) + 1], wb = ring[(mis >> 2) + 2], wc = ring[(mis >> 2) + 3], wd = ring[(mis >> 2) + 4];
         uint32_t z = __funnelshift_r(ring[mis >> 2], wa, pos), zh = __funnelshift_r(wa, wb, pos);
         const uint32_t c4440 = pl.sel_or;
         /* the length of a code from its two low bits: a byte table in a register read with one permute */
@@ -281,7 +285,9 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
             const bool cross = ((npos ^ pos) & 32u) != 0;   /* at most one word is left behind */
             wa = cross ? wb : wa;
             wb = cross ? wc : wb;
-            wc = lds32(ring_addr + ((npos >> 3) & (4 * RWORDS - 4)) + 12); /* the word after wb, crossed or not */
+            wc = cross ? wd : wc;
+            /* the second word after wb, crossed or not: asked for two words ahead, its latency has two windows to pass */
+            wd = lds32(ring_addr + ((npos >> 3) & (4 * RWORDS - 4)) + 16);
             zh = __funnelshift_r(wa, wb, npos);
             pos = npos;
         };
@@ -326,6 +332,10 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
                     for (uint32_t gi = 0; gi < gn; gi++) {
                         const uint32_t oldrung = rung_next, e = e_next;
                         const uint32_t gpos = pos;
+                        /* the old rung of the next group's band, asked for a whole group ahead; with one band it is this
+                           group's own rung */
+                        const uint32_t cnext = c + 1 == nbands ? 0 : c + 1;
+                        const uint32_t rung_ahead = rbs[cnext * 32 + lane];
                         const uint32_t swl = e >> 4, delta = e & 15;
                         /* a signal (a change flag with delta 0, QB3decode.h:619) opens a common factor or index group: the
                            walk below then runs on meaningless lengths, harmlessly, and the group is parsed again after it */
@@ -364,6 +374,7 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
                             pos = at;
                             const uint32_t wi = at >> 5;
                             wa = ring[(wi + 1) & (RWORDS - 1)]; wb = ring[(wi + 2) & (RWORDS - 1)]; wc = ring[(wi + 3) & (RWORDS - 1)];
+                        wd = ring[(wi + 4) & (RWORDS - 1)];
                             z = __funnelshift_r(ring[wi & (RWORDS - 1)], wa, at);
                             zh = __funnelshift_r(wa, wb, at);
                         };
@@ -388,11 +399,11 @@ __global__ void __launch_bounds__(384, 1) decode_kernel(const __grid_constant__ 
                             reopen(t.pos);
                         }
                         rbs[c * 32 + lane] = (uint8_t)r;
-                        c = c + 1 == bands ? 0 : c + 1;
-                        /* the next group's switch entry and old rung are asked for now: their latency passes behind the
-                           stores and the loop's end instead of ahead of the next group's first instruction */
+                        c = cnext;
+                        /* the next group's switch entry is asked for now: part of its latency passes behind the stores and the
+                           loop's end */
                         e_next = lds_u8(csb_sa + (z & ((4u << U) - 1)));
-                        rung_next = rbs[c * 32 + lane];
+                        rung_next = nbands == 1 ? r : rung_ahead;
                         rp[g0 + gi] = ((gpos - apos) << 4) | oldrung;
                     }
                 }

@@ -44,6 +44,7 @@ struct EncArgs {
     uint32_t is_signed, away;
     uint32_t vec_stage;   /* rows can be staged with 16 byte copies (no quantisation, no reorder) */
     uint32_t bulk_stage;  /* ... and every staged row is whole 16 byte units at a 16 byte address: bulk copies (TMA) */
+    uint32_t simd8;       /* ... and 8 bit data, at most four bands, width a multiple of four: byte SIMD front end */
     uint32_t rowpitch;    /* bytes between staged rows in shared memory, multiple of 16 */
     uint32_t win_words;   /* bit window size in 32 bit words */
     uint32_t best_off;    /* byte offset of the BEST mode scratch in shared memory, 8 byte aligned */

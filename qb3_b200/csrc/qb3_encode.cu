@@ -580,6 +580,17 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     uint32_t it = 0;
 
     const uint32_t blk = tid / a.bands, c = tid - blk * a.bands; /* this thread's block in the segment and band */
+    /* byte SIMD front end: pixel j of band k sits at byte j * bands + k of a block's row; selectors that pick the four
+       bytes of this thread's band, and of its core band, out of the row's four words */
+    uint32_t sel_own_lo = 0, sel_own_hi = 0, sel_own_m = 0, sel_core_lo = 0, sel_core_hi = 0, sel_core_m = 0;
+    if (BITS == 8 && a.simd8) {
+        const uint32_t cbk = a.cband[c < a.bands ? c : 0];
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t oo = j * a.bands + c, ok = j * a.bands + cbk;
+            sel_own_lo |= (oo & 7) << (4 * j); sel_own_hi |= (oo & 7) << (4 * j); sel_own_m |= (oo < 8 ? j : 4 + j) << (4 * j);
+            sel_core_lo |= (ok & 7) << (4 * j); sel_core_hi |= (ok & 7) << (4 * j); sel_core_m |= (ok < 8 ? j : 4 + j) << (4 * j);
+        }
+    }
     const uint32_t stage_bytes = 4 * a.rowpitch;
     /* segment (by, sg) -> staged rows; issued one segment ahead */
     /* Rows that are whole 16 byte units at 16 byte addresses (a.bulk_stage, decided by the host for the launch) travel
@@ -671,6 +682,52 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
                     prv = (W)q15[0] - ((W)q15[core_d] & dmask); /* only the low BITS bits matter from here on */
                 }
                 else prv = (W)carry_prev[par * a.bands + c] & TM;
+                if constexpr (BITS == 8 && CURVE != 0) {
+                  if (a.simd8) {
+                    /*
+                     * Byte SIMD front end (8 bit data, up to four bands, rows staged at 16 byte addresses, width a
+                     * multiple of four): a block's row is at most four words; the four pixels of this band are picked
+                     * out of them with three byte permutes (the selectors depend on band and band count only), the
+                     * core band likewise, and from there on four values travel per register: core band subtraction,
+                     * the curve order (one permute per four positions on the Hilbert and Z curves), the running delta
+                     * (the predecessor vector is the same words moved by a byte) and the sign folding.
+                     */
+                    uint32_t d[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(sbuf + rowoff[r] + (x0 - xs) * a.bands);
+                        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                        const uint32_t o = __byte_perm(__byte_perm(w0, w1, sel_own_lo), __byte_perm(w2, w3, sel_own_hi), sel_own_m);
+                        const uint32_t k = __byte_perm(__byte_perm(w0, w1, sel_core_lo), __byte_perm(w2, w3, sel_core_hi), sel_core_m);
+                        d[r] = __vsub4(o, k & (uint32_t)(0 - (uint32_t)(cb != c)));
+                    }
+                    uint32_t cv[4];
+                    if (CURVE == 1) { /* Hilbert 0x01548cd9aefb7623: positions (x, y) by fours */
+                        cv[0] = __byte_perm(d[0], d[1], 0x4510); cv[1] = __byte_perm(d[2], d[3], 0x1540);
+                        cv[2] = __byte_perm(d[2], d[3], 0x3762); cv[3] = __byte_perm(d[0], d[1], 0x3267);
+                    }
+                    else {            /* Z 0x0145236789cdabef */
+                        cv[0] = __byte_perm(d[0], d[1], 0x5410); cv[1] = __byte_perm(d[0], d[1], 0x7632);
+                        cv[2] = __byte_perm(d[2], d[3], 0x5410); cv[3] = __byte_perm(d[2], d[3], 0x7632);
+                    }
+                    uint32_t before = (uint32_t)prv << 24, mm[4], used4 = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t pv = __byte_perm(before, cv[k], 0x6543); /* the value ahead of each of the four */
+                        const uint32_t dl = __vsub4(cv[k], pv);
+                        /* mags per byte (QB3common.h:127-131): (d << 1) ^ (0xff where d is negative) */
+                        mm[k] = ((dl & 0x7f7f7f7fu) << 1) ^ (((dl >> 7) & 0x01010101u) * 0xffu);
+                        used4 |= mm[k];
+                        before = cv[k];
+                    }
+                    prv = cv[3] >> 24;
+                    used4 |= used4 >> 16;
+                    bitsused = (used4 | (used4 >> 8)) & 0xff;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) m[i] = __byte_perm(mm[i >> 2], 0u, 0x4440 + (i & 3));
+                  }
+                }
+                if (!(BITS == 8 && CURVE != 0 && a.simd8)) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     const uint32_t n = curve_pos<CURVE>(a.order, i);
@@ -679,6 +736,7 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
                     m[i] = mags_of_delta<BITS, W>(v - prv);
                     prv = v;
                     bitsused |= m[i];
+                }
                 }
                 rung = topbit((W)(bitsused | 1));
                 rung_s[tid] = (uint8_t)rung;

@@ -1356,6 +1356,8 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     if (err != cudaSuccess) return err;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int smem_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     const uint32_t bands = a.bands, nbx = (a.w + 3) / 4;
     FusePlan pl = {};
     pl.nwarps = 12; /* the scanner, two warps that leave its scheduler alone, nine that rebuild */
@@ -1397,10 +1399,20 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     size_t smem = layout(spc);
     while (smem > (size_t)smem_max && spc > 1) smem = layout(--spc);
     if (smem > (size_t)smem_max) return cudaErrorInvalidConfiguration;
+    pl.nsm = (uint32_t)nsm;
+    /* more streams than one CTA per SM takes: the build that fits two to an SM, when the shared memory does too, and
+       the streams spread evenly over whole waves of two CTAs per SM */
+    const bool dense = (a.ntiles + spc - 1) / spc > (uint32_t)nsm && 2 * (smem + 1024) <= (size_t)smem_sm;
+    if (dense) {
+        const uint32_t slots = 2 * (uint32_t)nsm, waves = (a.ntiles + 32 * slots - 1) / (32 * slots);
+        spc = (a.ntiles + slots * waves - 1) / (slots * waves);
+        smem = layout(spc);
+    }
     pl.spc = spc;
-    err = allow_max_smem<decode_kernel<T>>();
+    err = dense ? allow_max_smem<decode_kernel<T, true>>() : allow_max_smem<decode_kernel<T, false>>();
     if (err != cudaSuccess) return err;
-    decode_kernel<T><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
+    if (dense) decode_kernel<T, true><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
+    else decode_kernel<T, false><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
     launches += 1;
     return cudaGetLastError();
 }

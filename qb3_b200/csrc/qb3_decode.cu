@@ -333,21 +333,7 @@ __device__ __noinline__ bool read_special_group(S &s, W (&g)[16], uint8_t &rb, W
     return failed;
 }
 
-/* ------------------------------------------------------------------ two pass decode: scan, then rebuild */
-
-constexpr uint32_t ST_PARSED = 0x20000000u;   /* scan_kernel has written all of the tile's group records */
-constexpr uint32_t ST_SCANNING = 0x10000000u; /* scan_kernel is part way through the tile (the passes run in row chunks) */
-
-/* One chunk of block rows of every tile: the two passes are pipelined chunk by chunk on two streams. */
-struct RowChunk {
-    uint32_t by0, by1;  /* block rows [by0, by1) */
-    uint32_t first, last;
-};
-
-/* How a scan launch is laid out: several warps to a CTA, each with its own slice of shared memory. */
-struct ScanPlan {
-    uint32_t warp_smem; /* bytes of shared memory per warp, multiple of 16 */
-};
+constexpr uint32_t ST_SCANNING = 0x10000000u; /* decode_kernel has taken the tile (transient, never seen by a caller) */
 
 /* 16 bytes global -> shared, the tail beyond nbytes zero filled */
 __device__ __forceinline__ void cp_async16_zfill(uint32_t smem_addr, const void *gmem, uint32_t nbytes)
@@ -380,141 +366,7 @@ template <int RWORDS> struct RingBits {
     }
 };
 
-/*
- * Pass one for 32 and 64 bit types. Same job and same hand-over as scan_kernel -- one stream per lane, a record
- * (start bit << 6) | rung per group, reader state passed from row chunk to row chunk -- but the chain is kept simple:
- * a bit position, and per value the two low bits of its code read from the ring. These types have a quarter or an
- * eighth of the groups per byte of the 8 bit case, so the per group cost matters that much less.
- */
-template <typename T>
-__global__ void __launch_bounds__(128, 1) scan_wide_kernel(const DecArgs a, uint32_t *__restrict__ recs, const uint32_t ngroups,
-                                                           const RowChunk ch, unsigned long long *__restrict__ sstate,
-                                                           const ScanPlan plan)
-{
-    typedef typename traits<T>::W W;
-    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
-    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
-    constexpr int RWORDS = 256;                  /* ring words per lane */
-    constexpr int LSTRIDE = RWORDS + 4;
-    constexpr int EVERY = 2;                     /* groups between ring upkeeps */
-    constexpr int GWORDS = (16 * (BITS + 2) + 3 * BITS + 64) / 32 + 3; /* ring words one group of any kind can consume */
-    constexpr int AHEAD = RWORDS / 4 - 2;
-    static_assert(4 * (AHEAD - 1) >= 2 * EVERY * GWORDS + 4, "ring too small for two upkeep intervals");
-
-    extern __shared__ __align__(16) uint8_t smem_cta[];
-    const uint32_t lane = threadIdx.x & 31, wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), bands = a.bands;
-    if (wid * 32 >= a.ntiles) return;
-    uint8_t *smem = smem_cta + (threadIdx.x >> 5) * plan.warp_smem;
-    const uint32_t *ring = reinterpret_cast<const uint32_t *>(smem) + lane * LSTRIDE;
-    W *pcf = reinterpret_cast<W *>(smem + 32 * LSTRIDE * 4);              /* [band][lane] last common factor */
-    uint8_t *rb = reinterpret_cast<uint8_t *>(pcf + 32 * bands);           /* [band][lane] running rung */
-    uint8_t *cbs = rb + 32 * bands;                                        /* [band][lane] band map, header parsing only */
-    uint16_t *dsw = reinterpret_cast<uint16_t *>(cbs + 32 * bands + ((32 * bands) & 1)); /* rung switch decode table */
-    for (uint32_t i = lane; i < (2u << U); i += 32) dsw[i] = (uint16_t)ds_entry(U, i);
-
-    const uint32_t tile = wid * 32 + lane;
-    const bool live = tile < a.ntiles;
-    const uint8_t *stream = nullptr;
-    uint64_t slen = 0;
-    StreamInfo info;
-    info.order = 0; info.quanta = 1; info.mode = 0; info.data_off = 0; info.has_cb = 0; info.bad = 1;
-    if (live) {
-        stream = a.streams + a.offsets[tile];
-        slen = a.lens[tile];
-        parse_header(stream, slen, a, info, cbs + lane, 32);
-    }
-    const bool rle = info.mode == 2 || info.mode == 3 || info.mode == 6 || info.mode == 7;
-    const bool go = live && !info.bad && info.mode != M_STORED && !rle;
-    if (live && ch.first) a.status[tile] = go ? ST_SCANNING : info.bad ? (uint32_t)QB3CU_TILE_BAD_HEADER : ST_DEFER;
-
-    const uint8_t *payload = go ? stream + info.data_off : nullptr;
-    const uint64_t plen = go ? slen - info.data_off : 0;
-    const uint32_t mis = (uint32_t)((uintptr_t)payload & 15);
-    const uint8_t *abase = go ? payload - mis : a.streams;
-    const uint32_t span = go ? (uint32_t)(mis + plen) : 0;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem) + lane * LSTRIDE * 4;
-    unsigned long long *st = sstate + (size_t)(live ? tile : 0) * (2 + 2 * bands);
-    const bool resume = !ch.first && go;
-    RingBits<RWORDS> s;
-    s.ring = ring;
-    s.pos = resume ? (uint32_t)st[0] : 8 * mis;
-    bool failed = resume ? st[1] != 0 : false;
-    uint32_t issued = s.pos >> 7;
-    auto request = [&]() {
-        const uint32_t start = 16 * issued;
-        const uint32_t nbytes = start >= span ? 0u : min(16u, span - start);
-        cp_async16_zfill(ring_addr + (start & (4 * RWORDS - 1)), abase + (nbytes ? start : 0), nbytes);
-        issued++;
-    };
-    for (int i = 0; i < AHEAD; i++) request();
-    cp_async_commit();
-    cp_async_wait<0>();
-    for (uint32_t c = 0; c < bands; c++) {
-        rb[c * 32 + lane] = resume ? (uint8_t)st[2 + c] : (uint8_t)0;
-        pcf[c * 32 + lane] = resume ? (W)st[2 + bands + c] : (W)0;
-    }
-    __syncwarp();
-
-    const bool ftl = info.mode == M_FTL;
-    uint32_t *rec = recs + (size_t)(live ? tile : 0) * ngroups;
-    const uint32_t per_row = ((a.w + 3) / 4) * bands;
-    uint32_t c = 0, upkeep = 1;
-    const uint32_t g_begin = ch.by0 * per_row, g_end = ch.by1 * per_row;
-    for (uint32_t g = g_begin; g < g_end; g++) {
-        if (--upkeep == 0) {
-            upkeep = EVERY;
-            const uint32_t want = (s.pos >> 7) + AHEAD;
-            while (__any_sync(0xffffffffu, issued < want)) {
-                if (issued < want) request();
-            }
-            cp_async_commit();
-            cp_async_wait<1>();
-        }
-        const uint32_t oldrung = rb[c * 32 + lane];
-        const uint32_t pos = s.pos - 8 * mis;
-        const uint32_t x = s.peek32();
-        const uint32_t cs = (x & 1) ? dsw[(x >> 1) & LMASK] : 0u;
-        s.pos += (x & 1) ? cs >> 12 : 1;
-        uint32_t r;
-        if (ftl || (cs & 0xfff) != 0 || cs == 0) {
-            r = (oldrung + cs) & UMASK;
-            if (r == 0) s.pos += (s.peek32() & 1) ? 17 : 1; /* reference: QB3decode.h:148-160 */
-            else {
-#pragma unroll 4
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t y = s.peek32();
-                    const uint32_t b0 = y & 1, t = b0 & (y >> 1);
-                    s.pos += r + b0 + t;
-                }
-            }
-        }
-        else { /* common factor or index group: parsed in full, it is rare */
-            W sg[16];
-            uint8_t rbv = (uint8_t)oldrung;
-            W pc = pcf[c * 32 + lane];
-            RingBits<RWORDS> t = s;
-            failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
-            s.pos = t.pos;
-            pcf[c * 32 + lane] = pc;
-            r = rbv;
-        }
-        rb[c * 32 + lane] = (uint8_t)r;
-        if (go) rec[g] = (pos << 6) | r;
-        c = c + 1 == bands ? 0 : c + 1;
-    }
-    cp_async_wait<0>();
-    if (go && ch.last) {
-        const uint64_t total = 8 * plen, used = s.pos - 8 * mis;
-        const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
-        a.status[tile] = bad ? (uint32_t)QB3CU_TILE_CORRUPT : ST_PARSED;
-    }
-    else if (go) {
-        st[0] = s.pos; st[1] = failed;
-        for (uint32_t c2 = 0; c2 < bands; c2++) { st[2 + c2] = rb[c2 * 32 + lane]; st[2 + bands + c2] = pcf[c2 * 32 + lane]; }
-    }
-}
-
-/* Bit reader of rebuild_kernel: a thread reads one group at a known bit position straight from global memory
+/* Bit reader of the rebuild warps' general path: a thread reads one group at a known bit position straight from global memory
    (neighbouring threads read neighbouring words). Same contract as the others: 33 valid bits after refill(), zeros
    past the end of the payload. */
 struct GroupBits {
@@ -603,305 +455,6 @@ struct WideBits {
         return v;
     }
 };
-
-/*
- * Per band scan over the threads of a segment, thread t = block * bands + band: warp w takes bands w, w + nwarps, ...
- * and runs along the band's blocks 32 at a time. ADD: exclusive prefix sum of val, seeded and continued by carry[band].
- * LAST: the val of the latest earlier thread of the band with flag set, else carry[band]; carry moves on likewise.
- * val_s / flag_s are shared arrays indexed by thread; results replace val_s. Call with all threads, between barriers.
- */
-template <bool LAST, typename V>
-__device__ __forceinline__ void band_scan(V *val_s, const uint8_t *flag_s, V *carry, uint32_t nblk, uint32_t bands)
-{
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (uint32_t c = warp; c < bands; c += nwarps) {
-        V run = carry[c];
-        for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
-            const uint32_t b = b0 + lane, t = b * bands + c;
-            const bool in = b < nblk;
-            V v = in ? val_s[t] : (V)0;
-            if (!LAST) {
-                V inc = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const V o = __shfl_up_sync(0xffffffffu, inc, d);
-                    if (lane >= d) inc += o;
-                }
-                if (in) val_s[t] = run + inc - v;
-                run += __shfl_sync(0xffffffffu, inc, 31);
-            }
-            else {
-                uint32_t f = in && flag_s[t] ? 1u : 0u;
-                /* inclusive "last flagged" scan */
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const V ov = __shfl_up_sync(0xffffffffu, v, d);
-                    const uint32_t of = __shfl_up_sync(0xffffffffu, f, d);
-                    if (lane >= d && !f) { v = ov; f = of; }
-                }
-                /* exclusive: what the previous lane ended with */
-                const V pv = __shfl_up_sync(0xffffffffu, v, 1);
-                uint32_t pf = __shfl_up_sync(0xffffffffu, f, 1);
-                if (lane == 0) pf = 0;
-                if (in) val_s[t] = pf ? pv : run;
-                const V lv = __shfl_sync(0xffffffffu, v, 31);
-                const uint32_t lf = __shfl_sync(0xffffffffu, f, 31);
-                if (lf) run = lv;
-            }
-        }
-        if (lane == 0) carry[c] = run;
-    }
-}
-
-/*
- * Pass two, 8 and 16 bit types: with every group's start bit and rung known (scan_kernel), a tile decodes in parallel.
- * One CTA per tile walks it a segment (a run of blocks of one block row, all bands) at a time, one thread per group:
- *   1. the thread parses its group at its recorded position: values, step undo, sign unfolding, and the running sum
- *      inside the group (QB3decode.h:603-722 for one group)
- *   2. a per band scan of the group totals, seeded by the band's running value, gives every group its predecessor
- *      (the decoder's prv, QB3decode.h:717-722); common factor groups that reuse the band's factor get it from a
- *      "last written" scan of the same shape
- *   3. pixels are scattered into four staged rows in shared memory; there the core band is added to the derived
- *      bands (QB3decode.h:730-737) and quanta multiplied (QB3decode.cpp:77-107), and the rows leave as 16 byte vectors
- */
-template <typename T>
-__global__ void __launch_bounds__(sizeof(T) <= 2 ? 384 : 256, 2)
-rebuild_kernel(const DecArgs a, const uint32_t *__restrict__ recs, const uint32_t ngroups, const uint32_t seg_blocks,
-               const uint32_t segs, const uint32_t rowpitch, const RowChunk ch, unsigned long long *__restrict__ rstate)
-{
-    typedef typename traits<T>::W W;
-    constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
-    constexpr bool NARROW = BITS <= 16;
-    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
-    constexpr uint32_t RBITS = NARROW ? 4 : 6, RMASK = (1u << RBITS) - 1; /* record = (start bit << RBITS) | rung */
-    const W TM = (W)lowmask64(BITS);
-    typedef typename std::conditional<NARROW, GroupBits, WideBits>::type Bits;
-
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, NT = blockDim.x, tile = blockIdx.x, bands = a.bands;
-    uint8_t *stage = smem;                                                  /* [4][rowpitch] */
-    W *val_s = reinterpret_cast<W *>(stage + 4 * rowpitch);                 /* [NT] */
-    W *carry_prev = val_s + NT;                                             /* [bands] */
-    W *carry_pcf = carry_prev + bands;                                      /* [bands] */
-    uint8_t *flag_s = reinterpret_cast<uint8_t *>(carry_pcf + bands);       /* [NT] */
-    uint8_t *cb = flag_s + NT;                                              /* [bands] */
-    __shared__ StreamInfo info;
-    __shared__ uint32_t bandflags; /* 1: some band is derived, 2: a core band is itself derived (only hand made streams) */
-    __shared__ uint16_t dsw[2u << U]; /* rung switch decode table */
-    constexpr int VPR = BITS == 8 ? 3 : 2; /* values per refill: 3 * 9 and 2 * 16 bits fit the 33 a refill guarantees */
-
-    const uint32_t tile_state = a.status[tile];
-    if (tile_state != ST_PARSED && tile_state != ST_SCANNING) return;
-    unsigned long long *rst = rstate + (size_t)tile * 2 * bands; /* the bands' running value and factor between row chunks */
-    const uint8_t *stream = a.streams + a.offsets[tile];
-    const uint64_t slen = a.lens[tile];
-    if (tid == 0) {
-        parse_header(stream, slen, a, info, cb, 1);
-        uint32_t d = 0;
-        for (uint32_t c = 0; c < bands; c++) {
-            const uint32_t k = cb[c];
-            if (k != c) d |= 1 | (cb[k] != k ? 2 : 0);
-        }
-        bandflags = d;
-    }
-    for (uint32_t c = tid; c < bands; c += NT) {
-        carry_prev[c] = ch.first ? (W)0 : (W)rst[c];
-        carry_pcf[c] = ch.first ? (W)0 : (W)rst[bands + c];
-    }
-    for (uint32_t i = tid; i < (2u << U); i += NT) dsw[i] = (uint16_t)ds_entry(U, i);
-    __syncthreads();
-    const bool derived = bandflags != 0;
-    /* the plain case adds the core band straight from the core band's thread's pixels; chained band maps and
-       quantised derived bands go through the reference's per pixel sweep instead */
-    const bool sweep = (bandflags & 2) || (derived && info.quanta > 1);
-    const uint8_t *payload = stream + info.data_off;
-    const uint64_t plen = slen - info.data_off;
-    const uint64_t order = info.order ? info.order : HILBERT, quanta = info.quanta;
-    const bool ftl = info.mode == M_FTL, is_signed = a.dtype & 1;
-    const uint32_t *rec = recs + (size_t)tile * ngroups;
-    T *out = reinterpret_cast<T *>(a.dst + (uint64_t)tile * a.dst_pitch);
-    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4;
-    const uint32_t blk = tid / bands, c = tid - blk * bands;
-    const uint32_t rowelems = rowpitch / (uint32_t)sizeof(T);
-    const uint32_t core = cb[c < bands ? c : 0];
-    uint32_t poff[16]; /* where the 16 values of a block go in the staged rows */
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t n = (uint32_t)(order >> (4 * (15 - i))) & 15;
-        poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
-    }
-
-    for (uint32_t by = ch.by0; by < ch.by1; by++) {
-        const uint32_t y0 = min(4 * by, a.h - 4);
-        for (uint32_t sg = 0; sg < segs; sg++) {
-            const uint32_t bx0 = sg * seg_blocks, nblk = min(seg_blocks, nbx - bx0), ng = nblk * bands;
-            const uint32_t xs = min(4 * bx0, a.w - 4), xe = min(4 * (bx0 + nblk), a.w);
-            const bool active = tid < ng;
-            const uint32_t g = (by * nbx + bx0) * bands + tid;
-
-            W v[16];
-            W tot = 0;
-            uint32_t kind = 0; /* 1: common factor group that reuses the band's factor, 2: one that wrote a new factor */
-            uint32_t oldrung = 0, pos = 0;
-            if (active) {
-                pos = rec[g] >> RBITS;
-                oldrung = g >= bands ? rec[g - bands] & RMASK : 0;
-                Bits s;
-                s.open(payload, plen, pos);
-                uint32_t cs = 0;
-                {
-                    const uint32_t x = (uint32_t)s.peek(); /* narrow: open() left at least 33 bits */
-                    if (x & 1) cs = dsw[(x >> 1) & LMASK];
-                    s.advance((x & 1) ? cs >> 12 : 1);
-                }
-                if (ftl || (cs & 0xfff) != 0 || cs == 0) {
-                    const uint32_t r = (oldrung + cs) & UMASK;
-                    if constexpr (!NARROW) read_group<W>(s, r, v, !ftl); /* reference: QB3decode.h:142-290 */
-                    else {
-                    if (r == 0) {
-                        s.refill();
-                        const uint32_t y = (uint32_t)s.buf;
-                        const uint32_t b = (y & 1) ? (y >> 1) & 0xffffu : 0u;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = (b >> i) & 1;
-                    }
-                    else {
-                        const uint32_t half = 1u << (r - 1), fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
-                        const bool every = BITS == 16 && r == 15; /* two 17 bit codes exceed what one refill promises */
-                        uint32_t M = 0;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            if (i % VPR == 0 || every) s.refill();
-                            const uint32_t x = (uint32_t)s.buf;
-                            const uint32_t b0 = x & 1, t = b0 & (x >> 1), ht = half << t;
-                            uint32_t val = ((x >> (1 + b0)) & (ht - 1)) | ((half & (0u - b0)) << t);
-                            s.advance(r + b0 + t);
-                            if (val - fm1 <= 1u) val ^= sm; /* middle swap at rungs 1..7 */
-                            v[i] = val;
-                            M |= ((val >> r) & 1u) << i;
-                        }
-                        if (!ftl) {
-                            const int k = step_decode_index(M);
-#pragma unroll
-                            for (int i = 0; i < 16; i++) if (i == k) v[i] ^= 1u << r;
-                        }
-                    }
-                    }
-                }
-                else { /* common factor or index group; a reused factor is not known yet: parse with 0, redo below */
-                    Bits t = s;
-                    uint8_t rbv = (uint8_t)oldrung;
-                    W pc = 0;
-                    W sgv[16]; /* the out-of-line parser takes an array by reference: keep that one out of v's registers */
-                    read_special_group<W, BITS, U>(t, sgv, rbv, pc);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = sgv[i];
-                    /* what kind it was: the flag after the signal and the switch (QB3decode.h:624-640) */
-                    Bits p = s;
-                    const uint32_t e = ds_entry(U, (uint32_t)p.peek() & LMASK);
-                    p.advance((e >> 12) - 1);
-                    if (((oldrung + e) & UMASK) != UMASK) kind = p.get(1) ? 2 : 1;
-                    if (kind == 2) tot = pc; /* the factor this group wrote, for the scan */
-                }
-            }
-            /* bands' factors: only when a common factor group is around */
-            if (__syncthreads_or(kind != 0)) {
-                val_s[tid] = tot;
-                flag_s[tid] = kind == 2;
-                __syncthreads();
-                band_scan<true, W>(val_s, flag_s, carry_pcf, nblk, bands);
-                __syncthreads();
-                if (kind == 1) {
-                    Bits s;
-                    s.open(payload, plen, pos);
-                    s.advance(1 + (cs_signal(U) >> 12) - 1);
-                    uint8_t rbv = (uint8_t)oldrung;
-                    W pc = val_s[tid];
-                    W sgv[16];
-                    read_special_group<W, BITS, U>(s, sgv, rbv, pc);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = sgv[i];
-                }
-                __syncthreads();
-            }
-            /* running sum inside the group, then across the band's groups */
-            tot = 0;
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) { tot += smag<BITS, W>(v[i]); v[i] = tot; }
-            }
-            val_s[tid] = tot;
-            __syncthreads();
-            band_scan<false, W>(val_s, nullptr, carry_prev, nblk, bands);
-            __syncthreads();
-            const uint32_t npx = xe - xs;
-            T *p = reinterpret_cast<T *>(stage) + (size_t)(min(4 * (bx0 + blk), a.w - 4) - xs) * bands + c;
-            if (active) {
-                const W base = val_s[tid];
-#pragma unroll
-                for (int i = 0; i < 16; i++) v[i] += base;
-            }
-            if (sweep) { /* reference: QB3decode.h:730-737 (ascending bands, in place), QB3decode.cpp:434-450 */
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) p[poff[i]] = (T)v[i];
-                }
-                __syncthreads();
-                for (uint32_t i = tid; i < 4 * npx; i += NT) {
-                    const uint32_t r = i / npx, px = i - r * npx;
-                    T *q = reinterpret_cast<T *>(stage) + (size_t)r * rowelems + (size_t)px * bands;
-                    for (uint32_t k = 0; k < bands; k++) {
-                        const uint32_t kc = cb[k];
-                        if (kc != k) q[k] = (T)(q[k] + q[kc]);
-                    }
-                    if (quanta > 1)
-                        for (uint32_t k = 0; k < bands; k++)
-                            q[k] = (T)dequantize_value<BITS>((uint64_t)q[k], quanta, is_signed);
-                }
-            }
-            else {
-                /* core bands first, then the derived bands add their core band's pixels: the same 16 places, one band over */
-                if (active && core == c) {
-                    if (quanta > 1) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = (W)dequantize_value<BITS>((uint64_t)(v[i] & TM), quanta, is_signed);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i++) p[poff[i]] = (T)v[i];
-                }
-                if (derived) {
-                    __syncthreads();
-                    if (active && core != c) {
-                        const T *q = p + core - c;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) p[poff[i]] = (T)(v[i] + q[poff[i]]);
-                    }
-                }
-            }
-            __syncthreads();
-            /* staged rows leave as the widest vectors the destination allows */
-            const uint32_t rowbytes = npx * bands * (uint32_t)sizeof(T);
-            for (uint32_t r = 0; r < 4; r++) {
-                uint8_t *gp = reinterpret_cast<uint8_t *>(out + (uint64_t)(y0 + r) * a.stride + (uint64_t)xs * bands);
-                const uint8_t *sp = stage + r * rowpitch;
-                if ((((uintptr_t)gp | rowbytes) & 15) == 0)
-                    for (uint32_t j = 16 * tid; j < rowbytes; j += 16 * NT)
-                        st_stream16(gp + j, *reinterpret_cast<const uint4 *>(sp + j));
-                else if ((((uintptr_t)gp | rowbytes) & 3) == 0)
-                    for (uint32_t j = 4 * tid; j < rowbytes; j += 4 * NT)
-                        *reinterpret_cast<uint32_t *>(gp + j) = *reinterpret_cast<const uint32_t *>(sp + j);
-                else
-                    for (uint32_t j = sizeof(T) * tid; j < rowbytes; j += sizeof(T) * NT)
-                        *reinterpret_cast<T *>(gp + j) = *reinterpret_cast<const T *>(sp + j);
-            }
-            __syncthreads();
-        }
-    }
-    if (!ch.last) {
-        for (uint32_t c2 = tid; c2 < bands; c2 += NT) { rst[c2] = carry_prev[c2]; rst[bands + c2] = carry_pcf[c2]; }
-    }
-    else if (tid == 0 && tile_state == ST_PARSED) a.status[tile] = QB3CU_TILE_OK;
-}
 
 #include "qb3_decode_fused.cuh"
 
@@ -1092,175 +645,6 @@ cudaMemPool_t scratch_pool()
     return pools[dev];
 }
 
-/* Second stream of the two pass decode: one per caller stream and kind (a few are remembered per device), so that
-   batches decoded concurrently on different streams do not queue behind each other's kernels. high: with the highest
-   priority, for scans that run on SMs of their own; else of default priority, for rebuilds beside scans. */
-static cudaStream_t aux_stream(cudaStream_t user, bool high)
-{
-    struct Slot { cudaStream_t user, aux; bool used, high; };
-    static Slot slots[64][128] = {};
-    static cudaStream_t shared[64][2] = {}; /* for the callers that come when the table is full, one per kind */
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    int least = 0, greatest = 0;
-    cudaDeviceGetStreamPriorityRange(&least, &greatest);
-    Slot *free_slot = nullptr;
-    for (Slot &sl : slots[dev]) {
-        if (sl.used && sl.user == user && sl.high == high) return sl.aux;
-        if (!sl.used && !free_slot) free_slot = &sl;
-    }
-    if (!free_slot) {
-        /* Streams come and go (every QB3.h handle has its own) and the table never forgets: once it is full, later
-           callers share one stream per kind. Their batches then queue behind each other there, which is only slower. */
-        cudaStream_t &sh = shared[dev][high ? 1 : 0];
-        if (!sh && cudaStreamCreateWithPriority(&sh, cudaStreamNonBlocking, high ? greatest : least) != cudaSuccess) sh = nullptr;
-        return sh;
-    }
-    if (cudaStreamCreateWithPriority(&free_slot->aux, cudaStreamNonBlocking, high ? greatest : least) != cudaSuccess) return nullptr;
-    free_slot->user = user;
-    free_slot->used = true;
-    free_slot->high = high;
-    return free_slot->aux;
-}
-
-/*
- * scan_kernel + rebuild_kernel, pipelined: the tile batch is cut into chunks of block rows, scan runs chunk after
- * chunk on the caller's stream and hands its reader state on through memory, and the rebuild of a chunk starts on a
- * second stream as soon as its scan is done, so that it overlaps the scan of the following chunks. scan is latency
- * bound and leaves the SMs nearly empty; rebuild is throughput work that fills them. Plain stream / event ordering:
- * nothing ever spins on memory. The group records and the hand-over state live in stream ordered scratch memory.
- */
-template <typename T> static cudaError_t launch_scan_rebuild(const DecArgs &a, cudaStream_t st, uint32_t &launches)
-{
-    constexpr bool NARROW = sizeof(T) <= 2;
-    typedef typename traits<T>::W W;
-    const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, ngroups = nbx * nby * a.bands;
-    uint32_t nchunks = a.row_chunks ? a.row_chunks : a.rows_ready ? 16 : 12;
-    if (nchunks > 64) nchunks = 64;
-    if (nchunks > nby / 4) nchunks = nby / 4 ? nby / 4 : 1; /* four block rows per chunk on average, at least */
-    /*
-     * The scans run chunk after chunk on a stream of our own with the highest priority, the rebuilds on the caller's
-     * stream, each behind the scan of its chunk. When the batch leaves most SMs unused by the scan, its CTAs (four warps,
-     * one per warp scheduler) ask for a whole SM's shared memory, so that no rebuild CTA is ever co-resident with them:
-     * the serial parse is latency bound, and sharing its warp schedulers with the rebuild's warps costs it 15 %
-     * (measured). The priority makes the next chunk's scan CTAs take the SMs the last one's just left before the
-     * rebuild's thousands of CTAs get there.
-     */
-    uint8_t *scratch = nullptr;
-    cudaMemPool_t pool = scratch_pool();
-    const size_t rec_bytes = ((size_t)a.ntiles * ngroups * sizeof(uint32_t) + 15) & ~(size_t)15,
-                 ss_bytes = (size_t)a.ntiles * ((2 + 2 * a.bands) * 8 + 32), rs_bytes = (size_t)a.ntiles * 2 * a.bands * 8,
-                 total_bytes = rec_bytes + ss_bytes + rs_bytes;
-    cudaError_t err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), total_bytes, pool, st)
-                           : cudaMallocAsync(reinterpret_cast<void **>(&scratch), total_bytes, st);
-    if (err != cudaSuccess) return err;
-    uint32_t *recs = reinterpret_cast<uint32_t *>(scratch);
-    void *sstate = scratch + rec_bytes;
-    unsigned long long *rstate = reinterpret_cast<unsigned long long *>(scratch + rec_bytes + ss_bytes);
-
-    constexpr int RWORDS = sizeof(T) == 1 ? 64 : sizeof(T) == 2 ? 128 : 256;
-    size_t smem1 = NARROW ? (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * 6
-                          : (size_t)32 * (RWORDS + 4) * 4 + (size_t)32 * a.bands * (sizeof(W) + 2) + 2 + 2 * (2u << traits<T>::U);
-    smem1 = (smem1 + 15) & ~(size_t)15;
-    /* Scan CTAs: four warps (one per warp scheduler of an SM) with the SM's whole shared memory when that leaves two
-       thirds of the SMs to the rebuild; else a warp per CTA, spread over the SMs and sharing them with the rebuild. */
-    const uint32_t nwarps = (a.ntiles + 31) / 32;
-    int dev = 0, nsm = 0, smem_max = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    /* four warps to an SM only for 8 bit data: with the longer rings of the other types that many copies in flight per
-       SM slow each other down (measured: 16 bit scans take 1.8 times as long four to an SM) */
-    uint32_t wpc = 1;
-    while (wpc > 1 && wpc * smem1 > (size_t)smem_max) wpc >>= 1;
-    const bool own_sm = nchunks > 1 && !a.shared_sm && (int)((nwarps + wpc - 1) / wpc) * 3 <= nsm;
-    if (!own_sm) wpc = 1;
-    cudaStream_t aux = nchunks > 1 ? aux_stream(st, own_sm) : nullptr;
-    if (nchunks > 1 && !aux) { cudaFreeAsync(scratch, st); return cudaErrorUnknown; }
-    if (wpc > nwarps) wpc = nwarps;
-    const uint32_t scan_ctas = (nwarps + wpc - 1) / wpc;
-    const size_t scan_smem = own_sm ? (size_t)smem_max : wpc * smem1;
-
-    /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
-    const uint32_t max_threads = NARROW ? 384 : 256; /* what rebuild_kernel is built for */
-    uint32_t seg_blocks = max_threads / a.bands;
-    if (seg_blocks < 1) seg_blocks = 1;
-    if (seg_blocks > nbx) seg_blocks = nbx;
-    uint32_t segs = (nbx + seg_blocks - 1) / seg_blocks;
-    seg_blocks = (nbx + segs - 1) / segs;
-    segs = (nbx + seg_blocks - 1) / seg_blocks;
-    const uint32_t threads = (seg_blocks * a.bands + 31) & ~31u;
-    const uint32_t rowpitch = (seg_blocks * 4 * a.bands * (uint32_t)sizeof(T) + 15) & ~15u;
-    size_t smem2 = (size_t)4 * rowpitch + (size_t)threads * (sizeof(W) + 1) + (size_t)a.bands * (2 * sizeof(W) + 1) + 16;
-    err = allow_max_smem<scan_wide_kernel<T>>();
-    if (err == cudaSuccess) err = allow_max_smem<rebuild_kernel<T>>();
-
-    /* With SMs of their own the scans go to our high priority stream and the rebuilds stay on the caller's. Without,
-       the scans stay on the caller's stream, back to back, and the rebuilds go to the second stream: a scan launched
-       while a rebuild's CTAs are still being handed out gets its small CTAs packed onto the few SMs with room, many
-       warps to a scheduler, and runs four times slower (measured); following its predecessor in the same stream it
-       gets in before the rebuild that waits on an event. */
-    cudaStream_t sst = nchunks > 1 && own_sm ? aux : st, rst = nchunks > 1 && !own_sm ? aux : st;
-    auto order_after = [&](cudaStream_t later, cudaStream_t earlier) { /* later waits for what earlier holds now */
-        cudaEvent_t ev;
-        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-        e = cudaEventRecord(ev, earlier);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(later, ev, 0);
-        cudaEventDestroy(ev);
-        return e;
-    };
-    if (err == cudaSuccess && nchunks > 1) err = order_after(aux, st); /* the streams and the scratch memory are ready */
-    ScanPlan plan;
-    plan.warp_smem = (uint32_t)smem1;
-    /* Chunk sizes shrink geometrically: the rebuild of a chunk takes about 0.8 of its scan's time and cannot start
-       before that scan is over, so with each chunk 0.8 of the one before, every rebuild ends as the next scan does and
-       what is left after the last scan is the rebuild of a sliver (equal chunks leave a sixteenth of the rebuild). */
-    uint32_t bounds[65];
-    {
-        double w[64], sum = 0, acc = 0;
-        const double ratio = a.rows_ready ? 1.0 : 0.8; /* a caller that moves rows out as they complete wants them evenly */
-        for (uint32_t i = 0; i < nchunks; i++) sum += w[i] = i ? w[i - 1] * ratio : 1.0;
-        bounds[0] = 0;
-        for (uint32_t i = 0; i < nchunks; i++) {
-            acc += w[i];
-            uint32_t b = (uint32_t)(nby * acc / sum + 0.5);
-            const uint32_t lo = bounds[i] + 1, hi = nby - (nchunks - 1 - i); /* a block row at least for every chunk */
-            bounds[i + 1] = b < lo ? lo : b > hi ? hi : b;
-        }
-        bounds[nchunks] = nby;
-    }
-    for (uint32_t i = 0; i < nchunks && err == cudaSuccess; i++) {
-        RowChunk ch;
-        ch.by0 = bounds[i];
-        ch.by1 = bounds[i + 1];
-        ch.first = i == 0;
-        ch.last = i + 1 == nchunks;
-        scan_wide_kernel<T><<<scan_ctas, 32 * wpc, scan_smem, sst>>>(a, recs, ngroups, ch,
-                                                                     static_cast<unsigned long long *>(sstate), plan);
-        err = cudaGetLastError();
-        if (err == cudaSuccess && nchunks > 1) err = order_after(rst, sst);
-        if (err != cudaSuccess) break;
-        rebuild_kernel<T><<<a.ntiles, threads, smem2, rst>>>(a, recs, ngroups, seg_blocks, segs, rowpitch, ch, rstate);
-        err = cudaGetLastError();
-        launches += 2;
-        if (err == cudaSuccess && a.rows_ready) {
-            /* the last block row of an image whose height is not a multiple of four starts at h - 4 and rewrites
-               rows of the block row before it (QB3decode.h:331-333) */
-            const uint32_t row1 = ch.last ? a.h : 4 * ch.by1, row0 = ch.last && a.h - 4 < 4 * ch.by0 ? a.h - 4 : 4 * ch.by0;
-            a.rows_ready(a.rows_ctx, row0, row1, rst);
-        }
-    }
-    if (rst != st) { /* the caller's stream continues when the last rebuild is done */
-        const cudaError_t e2 = order_after(st, rst);
-        if (err == cudaSuccess) err = e2;
-    }
-    const cudaError_t ferr = cudaFreeAsync(scratch, st);
-    return err != cudaSuccess ? err : ferr;
-}
-
 /*
  * RLE streams (modes 2, 3, 6, 7) ahead of the two pass decode: a warp per stream expands the payload (deRLE0,
  * QB3decode.cpp:267-291) into a slot of scratch memory behind a copy of the headers whose mode byte names the plain
@@ -1350,7 +734,7 @@ __global__ void __launch_bounds__(128) derle_kernel(const DecArgs a, uint8_t *xb
  */
 template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStream_t st, uint32_t &launches)
 {
-    constexpr uint32_t RWORDS = FUSE_RWORDS(8 * sizeof(T));
+    constexpr uint32_t RWORDS = FUSE_RWORDS(8 * sizeof(T)), WB = FUSE_WBYTES(8 * sizeof(T));
     int dev = 0, nsm = 0, smem_max = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
@@ -1380,13 +764,13 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     auto layout = [&](uint32_t spc) -> size_t {
         auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
         size_t off = up((size_t)32 * (RWORDS + 4) * 4);
-        pl.off_band = (uint32_t)off; off = up(off + (size_t)32 * bands * 5);
+        pl.off_band = (uint32_t)off; off = up(off + (size_t)32 * bands * (WB + 1));
         pl.off_rec = (uint32_t)off;  off = up(off + (size_t)pl.nu * (spc + 1) * pl.rec_stride * 4);
         pl.off_info = (uint32_t)off; off = up(off + (size_t)spc * sizeof(FuseStream));
         pl.off_cb = (uint32_t)off;   off = up(off + (size_t)spc * bands);
-        pl.off_carry = (uint32_t)off; off = up(off + (size_t)2 * spc * bands * 4);
+        pl.off_carry = (uint32_t)off; off = up(off + (size_t)2 * spc * bands * WB);
         pl.off_stage = (uint32_t)off; off = up(off + (size_t)pl.rwarps * 4 * pl.rowpitch);
-        pl.off_tbl = (uint32_t)off;  off = up(off + 1024 + 2048 + 2 * 64 + 64);
+        pl.off_tbl = (uint32_t)off;  off = up(off + 1024 + 2048 + 1024); /* alignment slack, value table, the two switch tables */
         pl.off_bar = (uint32_t)off;  off = up(off + (size_t)2 * pl.nu * 8);
         return off;
     };
@@ -1447,21 +831,10 @@ template <typename T> static cudaError_t launch_decode_t(const DecArgs &a0, cuda
         uint8_t *p; cudaStream_t st;
         ~FreeLater() { if (p) cudaFreeAsync(p, st); }
     } free_later = {xscratch, st};
-    if (a.w >= 4 && a.h >= 4) {
-        if constexpr (sizeof(T) <= 2) { /* one fused kernel: a scanner warp and rebuild warps per CTA */
-            err = launch_fused<T>(a, st, launches);
-            if (err != cudaSuccess) return err;
-            walked = true;
-        }
-        else {
-            /* two passes when a group's start bit fits its record (26 bits); else the general path */
-            const uint64_t max_bits = 8 * (1024 + (uint64_t)16 * ((a.w + 3) / 4) * ((a.h + 3) / 4) * a.bands * (sizeof(T) + 1));
-            if (max_bits < (1ull << 26)) {
-                err = launch_scan_rebuild<T>(a, st, launches);
-                if (err != cudaSuccess) return err;
-                walked = true;
-            }
-        }
+    if (a.w >= 4 && a.h >= 4) { /* one fused kernel: a scanner warp and rebuild warps per CTA */
+        err = launch_fused<T>(a, st, launches);
+        if (err != cudaSuccess) return err;
+        walked = true;
     }
     const size_t smem = (size_t)32 * a.bands * (2 * sizeof(W) + 2);
     err = allow_max_smem<parse_kernel<T>>();

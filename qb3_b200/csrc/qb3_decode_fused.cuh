@@ -25,6 +25,7 @@
 #define QB3_B200_DECODE_FUSED_CUH
 
 #define FUSE_RWORDS(bits) ((bits) == 8 ? 256 : 512)
+#define FUSE_WBYTES(bits) ((bits) == 64 ? 8 : 4) /* sizeof(traits<T>::W) */
 
 struct FusePlan {
     uint32_t spc, rwarps;     /* streams per CTA (1..32), rebuild warps */
@@ -71,6 +72,12 @@ __device__ __forceinline__ int32_t lds_s8(uint32_t addr)
     asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 {
     uint32_t v;
@@ -82,15 +89,16 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
    stream. Parsed with the general reader; v gets the sign folded values. kind: 0 plain, 1 common factor group that
    reuses the band's factor (pc_in), 2 one that wrote a new factor (returned in pc_out). */
 template <typename T>
-__device__ __noinline__ void fuse_group_slow(const FuseStream &fs, uint64_t P, uint32_t oldrung, uint32_t pc_in,
-                                             uint32_t (&v)[16], uint32_t &kind, uint32_t &pc_out)
+__device__ __noinline__ void fuse_group_slow(const FuseStream &fs, uint64_t P, uint32_t oldrung, typename traits<T>::W pc_in,
+                                             typename traits<T>::W (&v)[16], uint32_t &kind, typename traits<T>::W &pc_out)
 {
-    typedef uint32_t W;
+    typedef typename traits<T>::W W;
+    typedef typename std::conditional<(traits<T>::BITS <= 16), GroupBits, WideBits>::type Bits;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
     constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
     const bool ftl = fs.flags & FS_FTL;
     const uint8_t *payload = reinterpret_cast<const uint8_t *>(fs.base) + fs.mis;
-    GroupBits s;
+    Bits s;
     s.open(payload, fs.plen, P - 8 * fs.mis);
     kind = 0; pc_out = 0;
     uint32_t cs = 0;
@@ -106,7 +114,7 @@ __device__ __noinline__ void fuse_group_slow(const FuseStream &fs, uint64_t P, u
         for (int i = 0; i < 16; i++) v[i] = g[i];
         return;
     }
-    GroupBits p = s; /* what kind it is: the flag after the signal and the switch (QB3decode.h:624-640) */
+    Bits p = s; /* what kind it is: the flag after the signal and the switch (QB3decode.h:624-640) */
     const uint32_t e = ds_entry(U, (uint32_t)p.peek() & LMASK);
     p.advance((e >> 12) - 1);
     if (((oldrung + e) & UMASK) != UMASK) kind = p.get(1) ? 2 : 1;
@@ -123,15 +131,19 @@ __device__ __noinline__ void fuse_group_slow(const FuseStream &fs, uint64_t P, u
 template <typename T, bool DENSE = false>
 __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid_constant__ DecArgs a, const __grid_constant__ FusePlan pl)
 {
-    typedef uint32_t W;
+    typedef typename traits<T>::W W;                     /* register type of a value */
+    typedef typename std::make_signed<W>::type SW;
     constexpr int BITS = traits<T>::BITS, U = traits<T>::U;
-    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1, TM = (1u << BITS) - 1;
+    constexpr bool NARROW = BITS <= 16;          /* 8 and 16 bit data: windowed scanner, table / arithmetic rebuild */
+    constexpr uint32_t UMASK = (1u << U) - 1, LMASK = 2 * UMASK + 1;
+    constexpr uint32_t RB = NARROW ? 4 : 6;      /* a record is (start bit << RB) | old rung */
+    const W TM = (W)lowmask64(BITS);
     constexpr int RWORDS = FUSE_RWORDS(BITS);    /* ring words per lane */
     constexpr int LSTRIDE = RWORDS + 4;          /* words between the rings of two lanes: banks shifted; the four spare
                                                     words mirror the ring's first four, so that a read of up to four
                                                     words on from any ring position never has to wrap */
-    constexpr int EVERY = 8;                     /* groups between ring upkeeps */
-    constexpr int GWORDS = BITS == 8 ? 7 : 12;   /* ring words one group of any kind can consume */
+    constexpr int EVERY = NARROW ? 8 : 2;        /* groups between ring upkeeps */
+    constexpr int GWORDS = BITS == 8 ? 7 : BITS == 16 ? 12 : BITS == 32 ? 22 : 40; /* ring words one group of any kind can consume */
     constexpr int AHEAD = RWORDS / 4 - 2;        /* chunks kept requested beyond the one being read */
     constexpr int DRAIN = EVERY * GWORDS / 4 + 1; /* chunks an upkeep interval can consume */
     constexpr int PENDING = 3;                   /* copy groups (one per upkeep) allowed in flight: a chunk requested at
@@ -145,28 +157,28 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bands = a.bands, spc = pl.spc;
     const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(smem);
-    uint32_t *pcfs = reinterpret_cast<uint32_t *>(smem + pl.off_band);             /* scanner: [band][32] last factor */
+    W *pcfs = reinterpret_cast<W *>(smem + pl.off_band);                           /* scanner: [band][32] last factor */
     uint8_t *rbs = reinterpret_cast<uint8_t *>(pcfs + 32 * bands);                 /* scanner: [band][32] running rung */
     uint32_t *recs = reinterpret_cast<uint32_t *>(smem + pl.off_rec);              /* [nu][spc + 1][rec_stride] */
     FuseStream *infos = reinterpret_cast<FuseStream *>(smem + pl.off_info);        /* [spc] */
     uint8_t *cbs = smem + pl.off_cb;                                               /* [spc][bands] band maps */
-    uint32_t *prevS = reinterpret_cast<uint32_t *>(smem + pl.off_carry);           /* rebuild: [spc][bands] running value */
-    uint32_t *pcfS = prevS + spc * bands;                                          /* rebuild: [spc][bands] last factor */
+    W *prevS = reinterpret_cast<W *>(smem + pl.off_carry);                         /* rebuild: [spc][bands] running value */
+    W *pcfS = prevS + spc * bands;                                                 /* rebuild: [spc][bands] last factor */
     const uint32_t tbl_sa = (smem_sa + pl.off_tbl + 1023) & ~1023u;                /* value table, 1 KB aligned: deltas, then flags */
     uint8_t *tbl = smem + (tbl_sa - smem_sa);
     uint16_t *dsw = reinterpret_cast<uint16_t *>(tbl + 2048);                      /* rung switch decode table */
-    uint8_t *csb = tbl + 2048 + 2 * (2u << U);                                     /* the same for the scanner, see below */
+    uint16_t *csb = reinterpret_cast<uint16_t *>(tbl + 2048 + 2 * (2u << U));      /* the same for the scanner, see below */
     const uint32_t bar_sa = smem_sa + pl.off_bar;                                  /* full[nu], empty[nu] */
 
     const uint32_t nbx = (a.w + 3) / 4, nby = (a.h + 3) / 4, nunits = nby * pl.upr;
 
     /* ---- set-up, all threads */
     for (uint32_t i = tid; i < (2u << U); i += blockDim.x) dsw[i] = (uint16_t)ds_entry(U, i);
-    /* scanner: (length << 4) | delta by the U + 2 low bits of a group, change flag included: an even index is "no
+    /* scanner: (length << 8) | delta by the U + 2 low bits of a group, change flag included: an even index is "no
        change", one bit long (QB3decode.h:98-116, 334) */
     for (uint32_t i = tid; i < (4u << U); i += blockDim.x) {
         const uint32_t d = ds_entry(U, i >> 1);
-        csb[i] = (i & 1) ? (uint8_t)(((d >> 12) << 4) | (d & 15)) : (uint8_t)0x10;
+        csb[i] = (i & 1) ? (uint16_t)(((d >> 12) << 8) | (d & 0xff)) : (uint16_t)0x100;
     }
     if (BITS == 8) {
         /* entry (4 << r) + x for the r + 2 low bits x of a code at rung r = 1..7: the sign-unfolded delta of the value
@@ -307,7 +319,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
         /* RARE: with the groups that are parsed again after the walk -- common factor and index groups, and the 16 bit
            groups at rung 15. A batch of FTL streams of 8 bit data has neither, and the loop without the check saves
            a branch with its reconvergence point per group. */
-        uint32_t e_next = lds_u8(csb_sa + (z & ((4u << U) - 1))), rung_next = 0;
+        uint32_t e_next = lds_u16(csb_sa + 2 * (z & ((4u << U) - 1))), rung_next = 0;
         auto walk = [&](auto rare_tag) {
             constexpr bool RARE = decltype(rare_tag)::value;
             for (uint32_t u = 0; u < nunits; u++) {
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                            group's own rung */
                         const uint32_t cnext = c + 1 == nbands ? 0 : c + 1;
                         const uint32_t rung_ahead = rbs[cnext * 32 + lane];
-                        const uint32_t swl = e >> 4, delta = e & 15;
+                        const uint32_t swl = e >> 8, delta = e & 0xff;
                         /* a signal (a change flag with delta 0, QB3decode.h:619) opens a common factor or index group: the
                            walk below then runs on meaningless lengths, harmlessly, and the group is parsed again after it */
                         const bool special = RARE && !ftl_l && delta == 0 && swl != 1;
@@ -352,9 +364,27 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                            raw bits (QB3decode.h:148-160) goes as the first value's length: 1 or 17 by the flag. Products, not
                            selects: a predicate takes three times as long to arrive as a register. */
                         const uint32_t nz = min(r, 1u);
-                        const uint32_t lens = nz * (0x02000100u + r * 0x01010101u);
+                        const uint32_t lens = nz * (0x02000100u + (NARROW ? r : 0u) * 0x01010101u);
                         const uint32_t lens_first = (nz ^ 1) * 0x11011101u + lens;
-                        {
+                        if constexpr (!NARROW) {
+                            /* 32 and 64 bit data: a code can be 65 bits, so no window is moved along. Value i starts at
+                               s + i * r + o_i with o_i <= 2 i, the bits it is longer than r by summed over the values before
+                               it: the 32 bits from s + i * r on hold its two low bits wherever it starts, and they are
+                               fetched for all sixteen values at once, ahead of the chain, which is then a shift, an AND, a
+                               permute and an add per value. lens is the table of the extra bits here (0, 1, 0, 2). */
+                            uint32_t b = gpos + swl, o = 0;
+    #pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                const uint32_t adr = ring_addr + ((b >> 3) & (4 * RWORDS - 4));
+                                const uint32_t lo = __funnelshift_r(lds32(adr), lds32(adr + 4), b);
+                                o += code_len(i ? lens : lens_first, __funnelshift_r(lo, 0u, o));
+                                b += r;
+                            }
+                            pos = b + o;
+                            const uint32_t adr = ring_addr + ((pos >> 3) & (4 * RWORDS - 4));
+                            z = __funnelshift_r(lds32(adr), lds32(adr + 4), pos);
+                        }
+                        else {
                             const uint32_t zs = z, zhs = zh;
                             uint32_t before = swl, len;
                             z >>= swl;
@@ -379,6 +409,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                         auto reopen = [&](uint32_t at) { /* the reader afresh at a ring position */
                             pos = at;
                             const uint32_t wi = at >> 5;
+                            if (!NARROW) { z = __funnelshift_r(ring[wi & (RWORDS - 1)], ring[(wi + 1) & (RWORDS - 1)], at); return; }
                             wa = ring[(wi + 1) & (RWORDS - 1)]; wb = ring[(wi + 2) & (RWORDS - 1)]; wc = ring[(wi + 3) & (RWORDS - 1)];
                         wd = ring[(wi + 4) & (RWORDS - 1)];
                             z = __funnelshift_r(ring[wi & (RWORDS - 1)], wa, at);
@@ -408,16 +439,16 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                         c = cnext;
                         /* the next group's switch entry is asked for now: part of its latency passes behind the stores and the
                            loop's end */
-                        e_next = lds_u8(csb_sa + (z & ((4u << U) - 1)));
+                        e_next = lds_u16(csb_sa + 2 * (z & ((4u << U) - 1)));
                         rung_next = nbands == 1 ? r : rung_ahead;
-                        rp[g0 + gi] = ((gpos - apos) << 4) | oldrung;
+                        rp[g0 + gi] = ((gpos - apos) << RB) | oldrung;
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_sa + 8 * slot);
             }
         };
-        if (BITS == 16 || __any_sync(0xffffffffu, go && !ftl_l)) walk(std::true_type());
+        if (BITS >= 16 || __any_sync(0xffffffffu, go && !ftl_l)) walk(std::true_type());
         else walk(std::false_type());
         cp_async_wait<0>();
         if (go) {
@@ -459,8 +490,8 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                 const uint32_t n = (uint32_t)(fs.order >> (4 * (15 - i))) & 15;
                 poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
             }
-            uint32_t carry = small_bands && lane < pl.gpi ? prevS[s * bands + lc] : 0u;
-            uint32_t *pcfc = pcfS + s * bands;
+            W carry = small_bands && lane < pl.gpi ? prevS[s * bands + lc] : (W)0;
+            W *pcfc = pcfS + s * bands;
 
             for (uint32_t it0 = 0; it0 < ng; it0 += pl.gpi) {
                 const uint32_t g = it0 + lane;
@@ -470,19 +501,21 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                 else { blk = g / bands; c = g - blk * bands; }
                 const uint32_t core = active ? cb[c] : c;
 
-                int32_t d[16];
-                uint32_t kind = 0, pcw = 0, oldrung = 0;
+                SW d[16]; /* the group's values, sign unfolded; then their running sums */
+                uint32_t kind = 0, oldrung = 0;
+                W pcw = 0;
                 uint64_t P = 0;
                 bool slow = false;
 #pragma unroll
                 for (int i = 0; i < 16; i++) d[i] = 0;
                 if (active) {
                     const uint32_t rc = rec[2 + g];
-                    oldrung = rc & 15;
-                    P = anchor + (rc >> 4);
+                    oldrung = rc & ((1u << RB) - 1);
+                    P = anchor + (rc >> RB);
                     const uint32_t widx = (uint32_t)(P >> 5), sh = (uint32_t)P & 31;
-                    slow = widx + NWL + 1 >= fs.nwords; /* the fast path never touches the stream's last word */
-                    if (!slow) {
+                    /* the fast path is for 8 and 16 bit data and never touches the stream's last word */
+                    slow = !NARROW || widx + NWL + 1 >= fs.nwords;
+                    if constexpr (NARROW) if (!slow) {
                         uint32_t wv[NWL + 1];
 #pragma unroll
                         for (int q = 0; q <= NWL; q++) wv[q] = __ldg(fs.base + widx + q);
@@ -498,7 +531,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                                 const uint32_t y = x >> swl;
                                 const uint32_t b = (y & 1) ? (y >> 1) & 0xffffu : 0u;
 #pragma unroll
-                                for (int i = 0; i < 16; i++) d[i] = -(int32_t)((b >> i) & 1);
+                                for (int i = 0; i < 16; i++) d[i] = -(SW)((b >> i) & 1);
                             }
                             else {
                                 const uint32_t lens = 0x02000100u + r * 0x01010101u;
@@ -521,7 +554,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                                         uint32_t val = ((z & ((1u << len) - 1)) >> shv) + half * (len - r);
                                         if (val - fm1 <= 1u) val ^= sm;
                                         if (!ftl) M += ((val >> r) & 1) << i;
-                                        d[i] = (int32_t)((val >> 1) ^ (0u - (val & 1)));
+                                        d[i] = (SW)((val >> 1) ^ (0u - (val & 1)));
                                     }
                                     z >>= len;
                                     used += len;
@@ -559,7 +592,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                                     if (kk >= 0) {
 #pragma unroll
                                         for (int i = 0; i < 16; i++)
-                                            if (i == kk) d[i] += d[i] < 0 ? -(int32_t)half : (int32_t)half;
+                                            if (i == kk) d[i] += d[i] < 0 ? -(SW)half : (SW)half;
                                     }
                                 }
                             }
@@ -567,11 +600,11 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                     }
                 }
                 if (__any_sync(FULL, slow)) { /* the rare groups, and the last few of a stream */
-                    uint32_t v[16];
-                    if (slow) fuse_group_slow<T>(fs, P, oldrung, 0, v, kind, pcw);
+                    W v[16];
+                    if (slow) fuse_group_slow<T>(fs, P, oldrung, (W)0, v, kind, pcw);
                     if (__any_sync(FULL, kind != 0)) {
                         /* the band's last written factor, in group order (QB3decode.h:629-640): rare enough for a walk */
-                        uint32_t mypc = 0;
+                        W mypc = 0;
                         for (uint32_t t = 0; t < pl.gpi; t++) {
                             if (lane == t && kind == 2) pcfc[c] = pcw;
                             if (lane == t && kind == 1) mypc = pcfc[c];
@@ -581,25 +614,25 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                     }
                     if (slow) {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) d[i] = (int32_t)((v[i] >> 1) ^ (0u - (v[i] & 1)));
+                        for (int i = 0; i < 16; i++) d[i] = (SW)((v[i] >> 1) ^ ((W)0 - (v[i] & 1)));
                     }
                 }
                 /* running sum inside the group, then across the band's groups */
-                uint32_t tot = 0;
+                W tot = 0;
 #pragma unroll
-                for (int i = 0; i < 16; i++) { tot += (uint32_t)d[i]; d[i] = (int32_t)tot; }
-                uint32_t base;
+                for (int i = 0; i < 16; i++) { tot += (W)d[i]; d[i] = (SW)tot; }
+                W base;
                 if (small_bands) {
-                    uint32_t inc = tot;
+                    W inc = tot;
                     for (uint32_t dd = bands; dd < pl.gpi; dd <<= 1) {
-                        const uint32_t o = __shfl_up_sync(FULL, inc, dd);
+                        const W o = __shfl_up_sync(FULL, inc, dd);
                         if (lane >= dd) inc += o;
                     }
                     base = carry + inc - tot;
                     carry += __shfl_sync(FULL, inc, (pl.bpi - 1) * bands + lc);
                 }
                 else {
-                    base = active ? prevS[s * bands + c] : 0u;
+                    base = active ? prevS[s * bands + c] : (W)0;
                     __syncwarp();
                     if (active) prevS[s * bands + c] = base + tot;
                 }
@@ -607,7 +640,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                 if (sweep) {
                     if (active) {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (uint32_t)d[i]);
+                        for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i]);
                     }
                 }
                 else {
@@ -617,11 +650,11 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                         if (quanta > 1) {
 #pragma unroll
                             for (int i = 0; i < 16; i++)
-                                p[poff[i]] = (T)dequantize_value<BITS>((uint64_t)((base + (uint32_t)d[i]) & TM), quanta, is_signed);
+                                p[poff[i]] = (T)dequantize_value<BITS>((uint64_t)((base + (W)d[i]) & TM), quanta, is_signed);
                         }
                         else {
 #pragma unroll
-                            for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (uint32_t)d[i]);
+                            for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i]);
                         }
                     }
                     if (derived) {
@@ -629,7 +662,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                         if (active && core != c) {
                             const T *q = p + (int)core - (int)c;
 #pragma unroll
-                            for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (uint32_t)d[i] + q[poff[i]]);
+                            for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i] + q[poff[i]]);
                         }
                     }
                 }

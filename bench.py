@@ -271,8 +271,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-tiles", type=int, default=0, help="tiles per end-to-end step (0: the resident leg's batch when host memory allows, else 2048)")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE configs")
-    ap.add_argument("--e2e-enc-chunk", type=int, default=128, help="tiles per chunk of the encode pipe")
-    ap.add_argument("--e2e-enc-depth", type=int, default=12, help="chunks in flight in the encode pipe")
+    ap.add_argument("--e2e-enc-chunk", type=int, default=256, help="tiles per chunk of the encode pipe")
+    ap.add_argument("--e2e-enc-depth", type=int, default=8, help="chunks in flight in the encode pipe")
     ap.add_argument("--e2e-dec-chunk", type=int, default=256, help="tiles per chunk of the decode pipe")
     ap.add_argument("--e2e-dec-depth", type=int, default=8, help="chunks in flight in the decode pipe")
     args = ap.parse_args()

@@ -79,16 +79,20 @@ size_t qb3cu_slot_bytes(const qb3cu_config *cfg)
 int qb3cu_last_cuda_error(void) { return g_last_cuda_error; }
 uint64_t qb3cu_kernel_launches(void) { return g_launches.load(); }
 
-int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch, void *d_dst,
+} /* extern "C" */
+
+/* qb3cu_encode_batch, and with size_only qb3cu_encoded_size_batch: the same launch with the packing left out */
+static int encode_impl(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch, void *d_dst,
                        size_t dst_slot_bytes, uint64_t *d_sizes, uint32_t *d_status, uint64_t *d_state,
-                       size_t ntiles, void *stream)
+                       size_t ntiles, void *stream, bool size_only)
 {
-    if (!geometry_ok(cfg) || cfg->mode > M_FTL || cfg->quanta < 1 || !d_src || !d_dst || !d_sizes) return QB3CU_ERR_PARAM;
+    if (!geometry_ok(cfg) || cfg->mode > M_FTL || cfg->quanta < 1 || !d_src || (!d_dst && !size_only) || !d_sizes) return QB3CU_ERR_PARAM;
     if (ntiles == 0) return QB3CU_OK;
     if (ntiles > 0x7fffffffull) return QB3CU_ERR_PARAM;
     const uint32_t tsize = TYPESIZE[cfg->dtype], bits = 8 * tsize;
     for (uint32_t c = 0; c < cfg->bands; c++) if (cfg->cband[c] >= cfg->bands) return QB3CU_ERR_PARAM;
     if (((uintptr_t)d_src | src_tile_pitch) % tsize) return QB3CU_ERR_PARAM;
+    if (size_only) dst_slot_bytes = qb3cu_slot_bytes(cfg);
     if (((uintptr_t)d_dst | dst_slot_bytes) % 16 || dst_slot_bytes < qb3cu_slot_bytes(cfg)) return QB3CU_ERR_PARAM;
     const uint64_t line = (uint64_t)cfg->width * cfg->bands;
     if (cfg->stride && cfg->stride < line) return QB3CU_ERR_PARAM;
@@ -109,6 +113,7 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     a.max_size = qb3cu_max_encoded_size(cfg);
     a.is_signed = cfg->dtype & 1;
     a.away = cfg->away != 0;
+    a.size_only = size_only;
     memcpy(a.cband, cfg->cband, sizeof(a.cband));
 
     /* mode: the RLE variants code as their base mode, RLE is a byte pass afterwards (reference: QB3encode.cpp:494-506) */
@@ -127,15 +132,31 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
     a.nby = (a.vh + 3) / 4;
     a.vec_stage = a.quanta == 1 && a.small == 0;
 
-    /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly */
-    const uint32_t max_threads = tsize <= 2 ? 512 : 256;
-    uint32_t seg_blocks = max_threads / a.bands;
-    if (seg_blocks < 1) seg_blocks = 1;
-    if (seg_blocks > a.nbx) seg_blocks = a.nbx;
-    a.segs = (a.nbx + seg_blocks - 1) / seg_blocks;
-    a.seg_blocks = (a.nbx + a.segs - 1) / a.segs;
-    a.segs = (a.nbx + a.seg_blocks - 1) / a.seg_blocks;
-    uint32_t threads = (a.seg_blocks * a.bands + 31) & ~31u;
+    /* one thread per group: as many whole blocks per iteration as fit the CTA, block rows split evenly. CTAs of up to
+       384 threads have builds that fit more of them on an SM (encode_kernel's DENSE: three instead of two for 8 bit
+       FTL / BASE, two instead of one for 8 and 16 bit BEST, Hilbert curve): the cap that puts more threads on an SM wins */
+    const bool best_mode = a.mode == M_CF_Z || a.mode == M_CF_H;
+    auto segments = [&](uint32_t max_threads) -> uint32_t {
+        uint32_t seg_blocks = max_threads / a.bands;
+        if (seg_blocks < 1) seg_blocks = 1;
+        if (seg_blocks > a.nbx) seg_blocks = a.nbx;
+        a.segs = (a.nbx + seg_blocks - 1) / seg_blocks;
+        a.seg_blocks = (a.nbx + a.segs - 1) / a.segs;
+        /* segments that start on 16 byte boundaries of the row can be staged by bulk copies */
+        uint32_t unit = 16, bb = 4 * a.bands * tsize;
+        while (bb % unit) unit >>= 1;
+        const uint32_t al = 16 / unit, up = (a.seg_blocks + al - 1) / al * al;
+        if (up <= seg_blocks) a.seg_blocks = up;
+        else if (a.seg_blocks >= al) a.seg_blocks = a.seg_blocks / al * al;
+        a.segs = (a.nbx + a.seg_blocks - 1) / a.seg_blocks;
+        return (a.seg_blocks * a.bands + 31) & ~31u;
+    };
+    uint32_t threads = segments(tsize <= 2 ? 512 : 256);
+    if (a.order == HILBERT && a.bands <= 384 && threads > 384 && (best_mode ? tsize <= 2 : tsize == 1)) {
+        const uint32_t wide = threads * (best_mode ? 1 : 2), dense = segments(384) * (best_mode ? 2 : 3);
+        if (dense < wide) segments(512);
+        threads = (a.seg_blocks * a.bands + 31) & ~31u;
+    }
     if (threads > 512) return QB3CU_ERR_PARAM;
     /* bulk copies (TMA) for the row staging when every segment's rows are whole 16 byte units at 16 byte addresses */
     a.bulk_stage = a.vec_stage && (((uintptr_t)d_src | src_tile_pitch | (a.stride * tsize)) & 15) == 0;
@@ -151,21 +172,22 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
                 + 2 * (size_t)a.bands + threads;
     smem = (smem + 7) & ~(size_t)7;
     a.best_off = (uint32_t)smem;
-    if (a.mode == M_CF_Z || a.mode == M_CF_H) smem += (size_t)threads * 8 + 2 * (size_t)a.bands * 8 + (size_t)threads * 4;
+    if (a.mode == M_CF_Z || a.mode == M_CF_H)
+        smem += (size_t)threads * 8 + 2 * (size_t)a.bands * 8 + (size_t)threads * 4 + 8 + (size_t)a.bands * 8 + 2 * (size_t)a.bands;
     smem = (smem + 7) & ~(size_t)7;
     a.lut_off = (uint32_t)smem;
     smem += 508 * 4 + 64 * 2;
     if (smem > 200 * 1024) return QB3CU_ERR_PARAM;
 
     /* Few large tiles: one CTA per tile would leave most of the GPU idle (a 4096 x 4096 tile alone takes 1.5 ms), so a
-       tile is cut into parts of whole block rows, a CTA each, and the parts' bits are joined afterwards. Not for BEST
-       (its last written factor has no bound on how far back it reaches). */
+       tile is cut into parts of whole block rows, a CTA each, and the parts' bits are joined afterwards. BEST needs a
+       second look at the parts that depended on the factor the parts before them left behind (EncArgs::best_pass). */
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint8_t *tmp = nullptr;
     const bool best = a.mode == M_CF_Z || a.mode == M_CF_H;
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (!best && a.small == 0 && a.nby >= 16 && ntiles < (size_t)4 * nsm) {
+    if (a.small == 0 && a.nby >= 16 && ntiles < (size_t)4 * nsm) {
         uint32_t parts = (uint32_t)(((size_t)6 * nsm + ntiles - 1) / ntiles); /* a few CTAs per SM to balance the load */
         if (parts > a.nby / 8) parts = a.nby / 8; /* eight block rows to a part at least */
         if (parts > 64) parts = 64;
@@ -175,13 +197,24 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
             const uint64_t groups = (uint64_t)a.part_rows * a.nbx * a.bands;
             a.tmp_slot = ((a.hdr_len + groups * max_group_bits(bits) / 8 + 64) + 15) & ~15ull;
             const size_t lens_bytes = (ntiles * a.parts * 8 + 15) & ~(size_t)15;
+            const size_t pcf_bytes = best ? ntiles * a.parts * a.bands * 32 : 0;
+            const size_t redo_bytes = best ? (ntiles * a.parts * 4 + 15) & ~(size_t)15 : 0;
             cudaMemPool_t pool = scratch_pool();
-            const size_t tmp_bytes = lens_bytes + a.tmp_slot * a.parts * ntiles;
+            const size_t tmp_bytes = lens_bytes + pcf_bytes + redo_bytes + (size_only ? 0 : a.tmp_slot * a.parts * ntiles);
             if (note_cuda(pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&tmp), tmp_bytes, pool, st)
                                : cudaMallocAsync(reinterpret_cast<void **>(&tmp), tmp_bytes, st)) != QB3CU_OK)
                 return QB3CU_ERR_CUDA;
             a.part_bits = reinterpret_cast<unsigned long long *>(tmp);
-            a.tmp = tmp + lens_bytes;
+            a.tmp = tmp + lens_bytes + pcf_bytes + redo_bytes;
+            if (best) {
+                a.best_pass = 1;
+                a.part_pcf = reinterpret_cast<unsigned long long *>(tmp + lens_bytes);
+                a.part_redo = reinterpret_cast<uint32_t *>(tmp + lens_bytes + pcf_bytes);
+                if (note_cuda(cudaMemsetAsync(a.part_redo, 0, redo_bytes, st)) != QB3CU_OK) {
+                    cudaFreeAsync(tmp, st);
+                    return QB3CU_ERR_CUDA;
+                }
+            }
         }
     }
     cudaError_t err = launch_encode(a, tsize, ntiles, threads, smem, st);
@@ -189,8 +222,35 @@ int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_ti
         const cudaError_t ferr = cudaFreeAsync(tmp, st);
         if (err == cudaSuccess) err = ferr;
     }
-    if (err == cudaSuccess) count_launches((a.rle_mode ? 2 : 1) + (a.parts > 1 ? 1 : 0));
+    if (err == cudaSuccess) count_launches((a.rle_mode ? 2 : 1) + (a.parts > 1 ? 1 : 0) + (a.parts > 1 && best ? 2 : 0));
     return note_cuda(err);
+}
+
+extern "C" {
+
+int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch, void *d_dst,
+                       size_t dst_slot_bytes, uint64_t *d_sizes, uint32_t *d_status, uint64_t *d_state,
+                       size_t ntiles, void *stream)
+{
+    return encode_impl(cfg, d_src, src_tile_pitch, d_dst, dst_slot_bytes, d_sizes, d_status, d_state, ntiles, stream, false);
+}
+
+int qb3cu_encoded_size_batch(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch, uint64_t *d_sizes,
+                             size_t ntiles, void *stream)
+{
+    if (!cfg || !rle_requested(cfg->mode))
+        return encode_impl(cfg, d_src, src_tile_pitch, nullptr, 0, d_sizes, nullptr, nullptr, ntiles, stream, true);
+    /* an RLE mode: whether the byte pass pays is only known once the bytes exist, so the streams are made, in scratch */
+    if (!geometry_ok(cfg) || ntiles == 0) return ntiles == 0 && geometry_ok(cfg) ? QB3CU_OK : QB3CU_ERR_PARAM;
+    const size_t slot = qb3cu_slot_bytes(cfg);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void *scratch = nullptr;
+    cudaMemPool_t pool = scratch_pool();
+    if (note_cuda(pool ? cudaMallocFromPoolAsync(&scratch, slot * ntiles, pool, st) : cudaMallocAsync(&scratch, slot * ntiles, st)) != QB3CU_OK)
+        return QB3CU_ERR_CUDA;
+    const int rc = encode_impl(cfg, d_src, src_tile_pitch, scratch, slot, d_sizes, nullptr, nullptr, ntiles, stream, false);
+    const int frc = note_cuda(cudaFreeAsync(scratch, st));
+    return rc != QB3CU_OK ? rc : frc;
 }
 
 int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,

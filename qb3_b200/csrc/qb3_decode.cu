@@ -744,8 +744,8 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     const uint32_t bands = a.bands, nbx = (a.w + 3) / 4;
     FusePlan pl = {};
-    pl.nwarps = 12; /* the scanner, two warps that leave its scheduler alone, nine that rebuild */
-    pl.rwarps = 9;
+    pl.nwarps = 12; /* the scanner, two warps that leave its scheduler alone, the feeder, eight that rebuild */
+    pl.rwarps = 8;
     pl.nu = 3;
     pl.sel_or = 0x4440;
     pl.bpi = bands <= 32 ? 32 / bands : 1;

@@ -146,13 +146,10 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
     constexpr int GWORDS = BITS == 8 ? 7 : BITS == 16 ? 12 : BITS == 32 ? 22 : 40; /* ring words one group of any kind can consume */
     constexpr int AHEAD = RWORDS / 4 - 2;        /* chunks kept requested beyond the one being read */
     constexpr int DRAIN = EVERY * GWORDS / 4 + 1; /* chunks an upkeep interval can consume */
-    constexpr int PENDING = 3;                   /* copy groups (one per upkeep) allowed in flight: a chunk requested at
-                                                    one upkeep is first read AHEAD / DRAIN upkeeps later at the earliest,
-                                                    which leaves its copy the time of 24 groups to arrive */
     constexpr int NV0 = BITS == 8 ? 3 : 1;       /* values that share a 32 bit window with the rung switch */
     constexpr int VPB = BITS == 8 ? 3 : 2;       /* values per window after that */
     constexpr int NWL = BITS == 8 ? 5 : 9;       /* words of a group's bits, aligned; one more is loaded */
-    static_assert(AHEAD / DRAIN - 1 >= PENDING, "ring too small for the copies allowed in flight");
+    static_assert(AHEAD >= 2 * DRAIN + 4, "ring too small for an upkeep interval");
 
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bands = a.bands, spc = pl.spc;
@@ -205,6 +202,13 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
        CTAs of odd waves take the warp before it, so that the two scanners of an SM sit on different schedulers. */
     const uint32_t scan_warp = pl.nwarps - 1 - (DENSE ? (blockIdx.x / pl.nsm) & 1 : 0);
     const bool scanner = warp == scan_warp;
+    /* The FEEDER, the warp before the scanner (another scheduler): keeps the scanner's rings filled, a lane per stream.
+       The scanner tells it where it reads (feed_cons, in 16 byte chunks), the feeder tells how far the ring is valid
+       (feed_fill). Filling its own ring cost the scanner a seventh of its instructions. */
+    const uint32_t feed_warp = scan_warp - 1;
+    __shared__ uint32_t feed_cons[32], feed_fill[32], feed_done;
+    if (tid < 32) { feed_cons[tid] = 0; feed_fill[tid] = 0; }
+    if (tid == 0) feed_done = 0;
     const bool live = scanner && lane < spc && tile < a.ntiles;
     bool go = false, ftl_l = false;
     uint32_t mis = 0, span = 0;
@@ -261,22 +265,19 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
            group's path (the compiler prefers to reload it) */
         uint32_t nbands;
         asm volatile("mov.u32 %0, %1;" : "=r"(nbands) : "r"(bands));
-        /* ring fill state: the next chunk's source, its place in the ring, the bytes of the stream left from there */
-        const uint8_t *rsrc = abase;
-        uint32_t rdst = 0, issued = 0;
-        int32_t rleft = (int32_t)span;
-        auto request = [&](bool on) {
-            const uint32_t nbytes = (uint32_t)min(max(rleft, 0), 16);
-            if (on) cp_async16_zfill(ring_addr + rdst, rsrc, nbytes);
-            if (on && rdst == 0) cp_async16_zfill(ring_addr + 4 * RWORDS, rsrc, nbytes); /* the mirror of the first four words */
-            if (on && rleft > 16) rsrc += 16; /* never points past the stream's last chunk */
-            rleft -= on ? 16 : 0;
-            rdst = (rdst + (on ? 16u : 0u)) & (4 * RWORDS - 1);
-            issued += on ? 1u : 0u;
+        /* how far the feeder has filled this lane's ring, as last seen; waited for whenever the reader could get there
+           before the next look */
+        volatile uint32_t *vfill = feed_fill, *vcons = feed_cons;
+        uint32_t fill_seen = 0;
+        auto upkeep = [&](uint32_t at_bit) {
+            vcons[lane] = at_bit >> 7;
+            const uint32_t need = (at_bit >> 7) + DRAIN + 2;
+            while (__any_sync(0xffffffffu, (int32_t)(fill_seen - need) < 0)) {
+                fill_seen = vfill[lane];
+                __threadfence_block();
+            }
         };
-        for (int i = 0; i < AHEAD; i++) request(true);
-        cp_async_commit();
-        cp_async_wait<0>();
+        upkeep(8 * mis);
         for (uint32_t cc = 0; cc < bands; cc++) { rbs[cc * 32 + lane] = 0; pcfs[cc * 32 + lane] = 0; }
         __syncwarp();
 
@@ -333,18 +334,9 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                 rp[1] = (uint32_t)(abs_bits >> 32);
                 rp += 2;
                 for (uint32_t g0 = 0; g0 < ng; g0 += EVERY) {
-                    /* ring upkeep every EVERY groups: request chunks up to AHEAD beyond the one being read; of the copy
-                       groups in flight all but the latest PENDING are waited for */
-                    {
-                        const uint32_t want = (pos >> 7) + 1 + AHEAD;
-                        /* as many rounds as the lane that is furthest behind needs, the same for every lane: one reduction, no
-                           vote and no divergent branch per request */
-                        const uint32_t rounds = __reduce_max_sync(0xffffffffu, want - issued);
-    #pragma unroll 1
-                        for (uint32_t q = 0; q < rounds; q++) request(issued < want);
-                        cp_async_commit();
-                        cp_async_wait<PENDING>();
-                    }
+                    /* ring upkeep every EVERY groups: the feeder hears where the reader is, and the reader makes sure the
+                       ring is valid as far as it can get before the next upkeep */
+                    upkeep(pos);
                     const uint32_t gn = min((uint32_t)EVERY, ng - g0);
     #pragma unroll 1
                     for (uint32_t gi = 0; gi < gn; gi++) {
@@ -450,7 +442,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
         };
         if (BITS >= 16 || __any_sync(0xffffffffu, go && !ftl_l)) walk(std::true_type());
         else walk(std::false_type());
-        cp_async_wait<0>();
+        if (lane == 0) *(volatile uint32_t *)&feed_done = 1;
         if (go) {
             const uint64_t total = 8 * plen, used = (uint32_t)(pos - 8 * mis);
             const bool bad = failed || (total > used && total - used > 7); /* reference: QB3decode.h:411,740 */
@@ -459,12 +451,47 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
         return;
     }
 
+    if (warp == feed_warp) {
+        /* ================================================================ feeder */
+        const bool has = lane < spc && infos[lane].base != nullptr;
+        const uint8_t *rsrc = has ? reinterpret_cast<const uint8_t *>(infos[lane].base) : a.streams;
+        int32_t rleft = has ? (int32_t)(infos[lane].mis + infos[lane].plen) : 0; /* bytes of the stream left from rsrc */
+        const uint32_t ring_addr = smem_sa + lane * LSTRIDE * 4;
+        uint32_t rdst = 0, issued = 0, before = 0;
+        volatile uint32_t *vfill = feed_fill, *vcons = feed_cons;
+        auto request = [&](bool on) { /* the next 16 bytes of the stream, zeros beyond its end, into the ring */
+            const uint32_t nbytes = (uint32_t)min(max(rleft, 0), 16);
+            if (on) cp_async16_zfill(ring_addr + rdst, rsrc, nbytes);
+            if (on && rdst == 0) cp_async16_zfill(ring_addr + 4 * RWORDS, rsrc, nbytes); /* the mirror of the first four words */
+            if (on && rleft > 16) rsrc += 16; /* never points past the stream's last chunk */
+            rleft -= on ? 16 : 0;
+            rdst = (rdst + (on ? 16u : 0u)) & (4 * RWORDS - 1);
+            issued += on ? 1u : 0u;
+        };
+        for (;;) {
+            /* chunks up to AHEAD beyond the one being read; as many rounds as the lane that is furthest behind needs */
+            const uint32_t want = vcons[lane] + 1 + AHEAD;
+            const uint32_t rounds = __reduce_max_sync(0xffffffffu, want - issued);
+#pragma unroll 1
+            for (uint32_t q = 0; q < rounds; q++) request(issued < want);
+            cp_async_commit();
+            cp_async_wait<1>(); /* everything but the copies just asked for has landed */
+            __threadfence_block();
+            vfill[lane] = before;
+            before = issued;
+            if (*(volatile uint32_t *)&feed_done) break;
+            if (rounds == 0) __nanosleep(256);
+        }
+        cp_async_wait<0>();
+        return;
+    }
+
     /* ==================================================================== rebuild warps */
     /* The scanner keeps its warp scheduler to itself: the warps that would share it (same warp id modulo 4) leave, the
        others are numbered 0 .. rwarps - 1. Whatever a rebuild warp issues there is taken from the one warp the whole
        CTA waits for. */
     if ((warp & 3) == (scan_warp & 3)) return;
-    const uint32_t rw = warp - (warp + 3 - (scan_warp & 3)) / 4, FULL = 0xffffffffu;
+    const uint32_t rw = warp - (warp + 3 - (scan_warp & 3)) / 4 - (warp > feed_warp ? 1 : 0), FULL = 0xffffffffu;
     const uint32_t rowpitch = pl.rowpitch, rowelems = rowpitch / (uint32_t)sizeof(T);
     uint8_t *stage = smem + pl.off_stage + (size_t)rw * 4 * rowpitch;
     const bool small_bands = bands <= 32;

@@ -56,6 +56,16 @@ struct EncArgs {
     uint64_t tmp_slot;          /* bytes per part region, multiple of 16 */
     uint8_t *tmp;
     unsigned long long *part_bits; /* [tile][part] bits written, all ones when the part did not fit */
+    /* BEST in parts. The band's last written factor reaches back without bound, so a part other than the first starts
+       without knowing it (best_pass 1) and notes per band which factors it met while it did not know (part_pcf:
+       [tile][part][band] x {factor going out, one if the part wrote one, mask of the factors that depended on the one
+       coming in (by their six low bits), factor coming in}); best_resolve_kernel then hands the factors down the parts
+       and marks in part_redo the parts that met the very factor that came in -- those are coded again knowing it
+       (best_pass 2). */
+    uint32_t best_pass;
+    uint32_t size_only;         /* nothing is packed or stored, only sizes[] is written (the band map search of cqb3 -m x) */
+    unsigned long long *part_pcf;
+    uint32_t *part_redo;        /* [tile][part] */
     uint8_t hdr[MAXHDR];        /* headers up to and including "DT", mode byte = mode */
     uint8_t hdr_stored[MAXHDR]; /* same for the stored fallback (mode 255, no CB / SC) */
     uint8_t cband[MAXBANDS];

@@ -507,6 +507,9 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     unsigned long long *cfm2_s = reinterpret_cast<unsigned long long *>(smem + a.best_off);            /* [blockDim] */
     unsigned long long *carry_pcf = cfm2_s + blockDim.x;                                               /* [2][bands] */
     int *commit_s = reinterpret_cast<int *>(carry_pcf + 2 * a.bands);                                  /* [blockDim] */
+    /* BEST in parts (EncArgs::best_pass): the factors met while the incoming one is unknown, and whether it still is */
+    unsigned long long *dep_mask = reinterpret_cast<unsigned long long *>(commit_s + blockDim.x + (blockDim.x & 1)); /* [bands] */
+    uint8_t *carry_unk = reinterpret_cast<uint8_t *>(dep_mask + a.bands);                              /* [2][bands] */
     /* 8 / 16 bit FTL and BASE: the rung 1..7 group codes (middle swap included) and the rung switches as shared
        tables, generated here from the closed forms; (len << 20) | bits and (len << 12) | bits */
     constexpr bool USE_LUT = !BEST && BITS <= 16;
@@ -523,12 +526,22 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     const uint32_t hdr_len = part == 0 ? a.hdr_len : 0;
     const bool use_step = a.mode != M_FTL;
 
+    if (BEST && a.best_pass == 2 && !a.part_redo[(uint64_t)tile * a.parts + part]) return; /* nothing depended on the factor coming in */
     /* running state in, zero unless the caller keeps it across calls (reference: QB3encode.h:391-394) */
     for (uint32_t c = tid; c < a.bands; c += NT) {
         const unsigned long long *st = a.state ? a.state + (uint64_t)tile * 3 * a.bands : nullptr;
         carry_prev[c] = st ? st[c] : 0ull;
         carry_rung[c] = st ? (uint8_t)st[a.bands + c] : (uint8_t)0;
-        if (BEST) carry_pcf[c] = st ? st[2 * a.bands + c] : 0ull;
+        if (BEST) {
+            carry_pcf[c] = st ? st[2 * a.bands + c] : 0ull;
+            if (a.best_pass) {
+                unsigned long long *pp = a.part_pcf + (((uint64_t)tile * a.parts + part) * a.bands + c) * 4;
+                if (a.best_pass == 2) carry_pcf[c] = pp[3];
+                if (a.best_pass == 1 && part == 0) pp[3] = carry_pcf[c];
+                carry_unk[c] = a.best_pass == 1 && part > 0;
+                dep_mask[c] = 0;
+            }
+        }
     }
     for (uint32_t i = tid; i < a.win_words; i += NT) win[i] = 0;
     if (HAVE_LUT) {
@@ -871,10 +884,16 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
                 if (active) {
                     const int before = blk > 0 ? commit_s[tid - a.bands] : -1;
                     const W pcf = (W)(before >= 0 ? cfm2_s[before] : carry_pcf[par * a.bands + c]);
-                    if (blk == nblk - 1)
+                    /* a later part of a tile, first pass: nobody has written a factor for this band yet in this part and
+                       the one the parts before leave behind is not known */
+                    const bool unk = a.best_pass && before < 0 && carry_unk[par * a.bands + c];
+                    if (unk && cf >= 2) atomicOr(&dep_mask[c], 1ull << ((uint32_t)cm2 & 63));
+                    if (blk == nblk - 1) {
                         carry_pcf[(par ^ 1) * a.bands + c] = last >= 0 ? cfm2_s[last] : carry_pcf[par * a.bands + c];
+                        if (a.best_pass) carry_unk[(par ^ 1) * a.bands + c] = last >= 0 ? (uint8_t)0 : carry_unk[par * a.bands + c];
+                    }
                     if (bitsused > 1) {
-                        same = cf >= 2 && pcf == cm2;
+                        same = cf >= 2 && pcf == cm2 && !unk;
                         const uint32_t sz = cf >= 2 ? (same ? l_same : l_diff) : l_plain;
                         kind = cf >= 2 ? 1 : 0;
                         len = sz;
@@ -893,6 +912,13 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
             const uint32_t s = wbits + off, e = s + len;
             Packer pk;
             pk.start(win, s);
+            if (a.size_only) { /* the lengths are all that is wanted */
+                const uint32_t Bq = wbits + total, nuq = Bq >> 7;
+                if ((flushed + nuq) * 16 > room) overflow = true;
+                flushed += nuq;
+                wbits = Bq & 127;
+                continue;
+            }
             if (BEST && active && kind != 0) {
                 typedef ValuePut<W, BITS> VP;
                 const uint32_t sig = cs_signal(U);
@@ -1015,10 +1041,18 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
 
     uint64_t len_bytes = flushed * 16 + ((wbits + 7) >> 3);
     if ((flushed + 1) * 16 > room) overflow = true;
-    if (wbits && !overflow && tid == 0)
+    if (wbits && !overflow && tid == 0 && !a.size_only)
         st_stream16(dst + flushed * 16, reinterpret_cast<const uint4 *>(win)[0]);
     if (multi) { /* stitch_kernel puts the parts together and settles size, status and the stored fallback */
         if (tid == 0) a.part_bits[(uint64_t)tile * a.parts + part] = overflow ? ~0ull : flushed * 128 + wbits;
+        if (BEST && a.best_pass == 1) {
+            for (uint32_t c = tid; c < a.bands; c += NT) {
+                unsigned long long *pp = a.part_pcf + (((uint64_t)tile * a.parts + part) * a.bands + c) * 4;
+                pp[0] = carry_pcf[(it & 1) * a.bands + c];
+                pp[1] = carry_unk[(it & 1) * a.bands + c] ? 0ull : 1ull;
+                pp[2] = dep_mask[c];
+            }
+        }
         return;
     }
 
@@ -1026,11 +1060,13 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     /* with an RLE mode the choice is left to rle_kernel: the reference tries RLE first (QB3encode.cpp:536-573) */
     if (a.small == 3 || overflow || (!a.rle_mode && a.raw_size <= len_bytes)) {
         __syncthreads();
-        for (uint32_t i = tid; i < a.hdr_stored_len; i += NT) dst[i] = a.hdr_stored[i];
         const uint64_t line = (uint64_t)a.w * a.bands * sizeof(T), pitch = a.stride * sizeof(T);
-        for (uint64_t i = tid; i < a.raw_size; i += NT) {
-            const uint64_t y = i / line, x = i - y * line;
-            dst[a.hdr_stored_len + i] = src[y * pitch + x];
+        if (!a.size_only) {
+            for (uint32_t i = tid; i < a.hdr_stored_len; i += NT) dst[i] = a.hdr_stored[i];
+            for (uint64_t i = tid; i < a.raw_size; i += NT) {
+                const uint64_t y = i / line, x = i - y * line;
+                dst[a.hdr_stored_len + i] = src[y * pitch + x];
+            }
         }
         len_bytes = a.hdr_stored_len + a.raw_size;
     }
@@ -1040,6 +1076,28 @@ __global__ void __launch_bounds__(DENSE ? 384 : 512, DENSE ? (BEST ? 2 : 3) : BE
     }
 }
 
+
+/* ------------------------------------------------------------------ BEST in parts: the factors handed down */
+
+/* One CTA per tile, a thread per band: walks the parts in order (EncArgs::part_pcf), gives every part the factor its
+   band starts from, and marks the parts that met that very factor while they did not know it. The tile's running
+   state gets the factor the last part leaves behind. */
+__global__ void __launch_bounds__(256) best_resolve_kernel(const __grid_constant__ EncArgs a)
+{
+    const uint32_t tile = blockIdx.x;
+    for (uint32_t c = threadIdx.x; c < a.bands; c += blockDim.x) {
+        unsigned long long *pp = a.part_pcf + ((uint64_t)tile * a.parts * a.bands + c) * 4;
+        unsigned long long cur = pp[3]; /* the first part knew where it started */
+        for (uint32_t q = 0; q < a.parts; q++, pp += 4 * (uint64_t)a.bands) {
+            if (q > 0) {
+                pp[3] = cur;
+                if ((pp[2] >> (cur & 63)) & 1) a.part_redo[(uint64_t)tile * a.parts + q] = 1;
+            }
+            if (pp[1]) cur = pp[0];
+        }
+        if (a.state) a.state[(uint64_t)tile * 3 * a.bands + 2 * a.bands + c] = cur;
+    }
+}
 
 /* ------------------------------------------------------------------ joining the parts of a tile */
 
@@ -1065,6 +1123,11 @@ __global__ void __launch_bounds__(256) stitch_kernel(const __grid_constant__ Enc
     const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
     const uint64_t len_bytes = (total + 7) >> 3;
     overflow |= ((len_bytes + 15) & ~15ull) > a.slot;
+    if (a.size_only) {
+        if (part == 0 && tid == 0)
+            a.sizes[tile] = overflow || (!a.rle_mode && a.raw_size <= len_bytes) ? a.hdr_stored_len + a.raw_size : len_bytes;
+        return;
+    }
     if (overflow || (!a.rle_mode && a.raw_size <= len_bytes)) {
         if (part == 0)
             for (uint32_t i = tid; i < a.hdr_stored_len; i += NT) dst[i] = a.hdr_stored[i];
@@ -1117,55 +1180,75 @@ __global__ void __launch_bounds__(256) stitch_kernel(const __grid_constant__ Enc
 /* ------------------------------------------------------------------ RLE0 byte pass */
 
 /*
- * RLE0 / RLE0Size (reference: QB3encode.cpp:271-332) by one warp: "FF FF" becomes "FF FF FF", four or more zero
- * bytes become "FF FF n" (n = count - 4, at most 0xfe) unless the byte emitted just before was a literal FF; the
- * last two bytes are always literal. The scanner is serial by nature, but between candidate positions (an equal
- * pair of 00 or FF) it moves one literal byte at a time, so a warp looks at 32 positions per step, copies the
- * literals in front of the first candidate together and only resolves candidates one by one.
- * out == nullptr only measures. Returns the output size (warp uniform).
+ * RLE0 / RLE0Size (reference: QB3encode.cpp:271-332): "FF FF" becomes "FF FF FF", four or more zero bytes become
+ * "FF FF n" (n = count - 4, at most 0xfe) unless the byte emitted just before was a literal FF; the last two bytes are
+ * always literal. The transducer is serial, but its state is forgotten at every byte that is neither 00 nor FF: such a
+ * byte can only leave as a literal, and after it the scanner stands at a token start knowing all it needs (the last
+ * byte out was not FF). So the data is cut into chunks that begin right after such a byte (rle_sync), the chunks are
+ * measured and written independently by the warps of a CTA, and a scan of the chunk sizes places them.
+ *
+ * rle_range works through [i0, e) of the n bytes at p, e a chunk start or n. 256 bytes a step, eight to a lane, as
+ * aligned words; a step without an equal pair of 00 or FF (nearly all of them, in a compressed stream) is found out
+ * with a few word operations and leaves as literals at once; otherwise the literals in front of the first candidate
+ * go together and the candidate is resolved on its own. out == nullptr only measures. Returns the output size
+ * (warp uniform).
  */
-__device__ static uint64_t rle_pass(const uint8_t *p, uint64_t n, uint8_t *out)
+__device__ static uint64_t rle_range(const uint8_t *p, uint64_t n, uint64_t i0, uint64_t e, uint8_t *out)
 {
     const uint32_t FULL = 0xffffffffu, lane = lane_id();
+    constexpr int BPL = 8;
     const uint64_t lim = n >= 2 ? n - 2 : 0; /* a pair or run cannot start in the last two bytes */
-    uint64_t i = 0, o = 0;
+    const uint64_t limr = lim < e ? lim : e;
+    uint64_t i = i0, o = 0;
     uint32_t last = 0;
-    while (i < lim) {
-        /* 256 bytes a step, eight to a lane: the loads of a step are independent of each other, and one step's latency
-           is paid for eight times the bytes of a byte per lane */
-        constexpr int BPL = 8;
+    while (i < limr) {
+        /* the lane's eight bytes from position i + 8 * lane: three aligned words, moved into place. Bytes past n may be
+           anything (they are inside the tile's slot): no position from limr on is ever a candidate, and literals are
+           counted, not taken on trust */
         const uint64_t pos = i + BPL * lane;
-        uint32_t b[BPL + 1];
+        const uint8_t *q = p + pos;
+        const uint32_t sh = 8 * (uint32_t)((uintptr_t)q & 3);
+        const uint32_t *qa = reinterpret_cast<const uint32_t *>(q - (sh >> 3));
+        const bool in = pos < n;
+        const uint32_t w0 = in ? qa[0] : 0x01010101u, w1 = in ? qa[1] : 0x01010101u, w2 = in ? qa[2] : 0x01010101u;
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+        uint32_t nx = __shfl_down_sync(FULL, x0, 1); /* the byte after the lane's eight */
+        if (lane == 31) nx = __funnelshift_r(w2, 0u, sh);
+        uint32_t k = 32 * BPL; /* first candidate of the step */
+        {
+            const uint32_t y0 = __funnelshift_r(x0, x1, 8), y1 = __funnelshift_r(x1, nx, 8); /* each byte's successor */
+            auto has_zero = [](uint32_t v) { return (v - 0x01010101u) & ~v & 0x80808080u; };
+            const uint32_t any = has_zero(x0 | y0) | has_zero(x1 | y1) | has_zero(~(x0 & y0)) | has_zero(~(x1 & y1));
+            if (__any_sync(FULL, any != 0) || i + 32 * BPL > limr) {
+                uint32_t b[BPL + 1];
 #pragma unroll
-        for (int j = 0; j < BPL; j++) b[j] = pos + j < n ? p[pos + j] : 1u;
-        b[BPL] = __shfl_down_sync(FULL, b[0], 1);
-        if (lane == 31) b[BPL] = pos + BPL < n ? p[pos + BPL] : 1u;
-        uint32_t k = 32 * BPL;
+                for (int j = 0; j < 4; j++) { b[j] = (x0 >> (8 * j)) & 0xff; b[4 + j] = (x1 >> (8 * j)) & 0xff; }
+                b[BPL] = nx & 0xff;
 #pragma unroll
-        for (int j = 0; j < BPL; j++) {
-            const bool cand = pos + j < lim && b[j] == b[j + 1] && (b[j] == 0 || b[j] == 0xff);
-            const uint32_t mask = __ballot_sync(FULL, cand);
-            if (mask) k = min(k, BPL * ((uint32_t)__ffs((int)mask) - 1) + j);
+                for (int j = 0; j < BPL; j++) {
+                    const bool cand = pos + j < limr && b[j] == b[j + 1] && (b[j] == 0 || b[j] == 0xff);
+                    const uint32_t mask = __ballot_sync(FULL, cand);
+                    if (mask) k = min(k, BPL * ((uint32_t)__ffs((int)mask) - 1) + j);
+                }
+            }
         }
         auto byte_at = [&](uint32_t idx) -> uint32_t { /* byte idx of the step (warp uniform idx) */
             const uint32_t j = idx % BPL;
-            uint32_t v = b[0];
-#pragma unroll
-            for (int t = 1; t < BPL; t++) if (j == (uint32_t)t) v = b[t];
+            const uint32_t v = ((j < 4 ? x0 : x1) >> (8 * (j & 3))) & 0xff;
             return __shfl_sync(FULL, v, idx / BPL);
         };
-        const uint32_t nlit = (uint32_t)min((uint64_t)k, lim - i);
+        const uint32_t nlit = (uint32_t)min((uint64_t)k, limr - i);
         if (nlit) {
             if (out) {
 #pragma unroll
                 for (int j = 0; j < BPL; j++)
-                    if (BPL * lane + j < nlit) out[o + BPL * lane + j] = (uint8_t)b[j];
+                    if (BPL * lane + j < nlit) out[o + BPL * lane + j] = (uint8_t)(((j < 4 ? x0 : x1) >> (8 * (j & 3))) & 0xff);
             }
             last = byte_at(nlit - 1);
             o += nlit;
             i += nlit;
         }
-        if (k == 32 * BPL) continue;
+        if (k == 32 * BPL || i >= limr) continue;
         const uint32_t c = byte_at(k); /* the candidate, now at position i */
         if (c == 0xff) {
             if (out && lane < 3) out[o + lane] = 0xff;
@@ -1181,8 +1264,8 @@ __device__ static uint64_t rle_pass(const uint8_t *p, uint64_t n, uint8_t *out)
         i += 4;
         uint32_t r = 0; /* zeros beyond the first four */
         for (;;) {
-            const uint64_t q = i + r + lane;
-            const bool z = q < n && r + lane < 0xfe && p[q] == 0;
+            const uint64_t qq = i + r + lane;
+            const bool z = qq < n && r + lane < 0xfe && p[qq] == 0;
             const uint32_t zm = __ballot_sync(FULL, z);
             const uint32_t here = zm == FULL ? 32 : (uint32_t)__ffs((int)~zm) - 1;
             r += here;
@@ -1191,41 +1274,81 @@ __device__ static uint64_t rle_pass(const uint8_t *p, uint64_t n, uint8_t *out)
         if (out && lane < 3) out[o + lane] = lane < 2 ? 0xff : (uint8_t)r;
         o += 3; i += r; last = 0;
     }
-    while (i < n) {
+    while (i < e) { /* the literal tail */
         const uint64_t pos = i + lane;
-        const uint32_t cnt = (uint32_t)min((uint64_t)32, n - i);
-        if (out && pos < n) out[o + lane] = p[pos];
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, e - i);
+        if (out && pos < e) out[o + lane] = p[pos];
         o += cnt; i += cnt;
     }
     return o;
 }
 
-/* One warp per tile, after encode_kernel, for the RLE modes only: RLE when it pays, else the stored check
-   (reference: QB3encode.cpp:536-573). */
-__global__ void __launch_bounds__(128) rle_kernel(const __grid_constant__ EncArgs a, uint32_t ntiles)
+/* the first chunk start at or after position from: a position whose predecessor is neither 00 nor FF; n when there
+   is none (warp uniform) */
+__device__ static uint64_t rle_sync(const uint8_t *p, uint64_t n, uint64_t from)
 {
-    const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
-    if (tile >= ntiles) return;
+    if (from == 0) return 0;
+    for (uint64_t q = from; q < n; q += 32) {
+        const uint64_t at = q + lane_id();
+        const uint32_t v = at <= n ? p[at - 1] : 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, at <= n && v != 0 && v != 0xff);
+        if (m) return q + (uint32_t)__ffs((int)m) - 1;
+    }
+    return n;
+}
+
+/* One CTA per tile, after encode_kernel, for the RLE modes only: RLE when it pays, else the stored check
+   (reference: QB3encode.cpp:536-573). */
+constexpr uint32_t RLE_THREADS = 512, RLE_MAXCHUNKS = 2048;
+__global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant__ EncArgs a, uint32_t ntiles)
+{
+    __shared__ uint32_t sync_s[RLE_MAXCHUNKS + 1]; /* chunk starts; streams are far below 4 GB (max_size / 2 of a 64K x 64K tile is not) */
+    __shared__ uint32_t size_s[RLE_MAXCHUNKS];
+    __shared__ uint32_t scratch[36];
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RLE_THREADS / 32;
     uint8_t *dst = a.dst + (uint64_t)tile * a.slot;
     const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
     if (dst[10] == M_STORED) return; /* already final */
     const uint64_t len = a.sizes[tile], hdr = a.hdr_len, data = len - hdr;
-    if (len <= a.max_size / 2) { /* "a vague limit", but it decides the bytes */
+    if (len <= a.max_size / 2 && data < 0xffffffffull) { /* "a vague limit", but it decides the bytes */
         const uint64_t avail = a.max_size - len;
-        const uint64_t rsz = rle_pass(dst + hdr, data, nullptr);
+        const uint8_t *p = dst + hdr;
+        /* chunks of at least 1 KB, at most RLE_MAXCHUNKS of them */
+        uint64_t csize = 1024;
+        while ((data + csize - 1) / csize > RLE_MAXCHUNKS) csize *= 2;
+        const uint32_t nch = (uint32_t)((data + csize - 1) / csize);
+        for (uint32_t k = warp; k < nch; k += nwarps) {
+            const uint64_t s = rle_sync(p, data, k * csize);
+            if (lane == 0) sync_s[k] = (uint32_t)s;
+        }
+        if (tid == 0) sync_s[nch] = (uint32_t)data;
+        __syncthreads();
+        for (uint32_t k = warp; k < nch; k += nwarps) {
+            const uint64_t s = sync_s[k], e = sync_s[k + 1];
+            const uint64_t z = s < e ? rle_range(p, data, s, e, nullptr) : 0;
+            if (lane == 0) size_s[k] = (uint32_t)z;
+        }
+        __syncthreads();
+        /* exclusive scan of the chunk sizes, RLE_THREADS at a time */
+        uint64_t rsz = 0;
+        for (uint32_t k0 = 0; k0 < nch; k0 += RLE_THREADS) {
+            const uint32_t k = k0 + tid, v = k < nch ? size_s[k] : 0u;
+            uint32_t total;
+            const uint32_t off = block_exclusive_scan(v, scratch, total);
+            __syncthreads();
+            if (k < nch) size_s[k] = (uint32_t)rsz + off; /* now the chunk's place in the output */
+            rsz += total;
+        }
+        __syncthreads();
         if (rsz <= avail && rsz < data) {
-            rle_pass(dst + hdr, data, dst + len); /* into the free tail of the slot, then down over the data */
-            __syncwarp();
-            /* down over the data; eight bytes a lane and step, loads before stores (the ranges do not overlap within a
-               step: the source is at least the data's length further on) */
-            for (uint64_t k0 = 0; k0 < rsz; k0 += 256) {
-                uint8_t t[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) { const uint64_t k = k0 + 8 * lane + j; t[j] = k < rsz ? dst[len + k] : 0; }
-#pragma unroll
-                for (int j = 0; j < 8; j++) { const uint64_t k = k0 + 8 * lane + j; if (k < rsz) dst[hdr + k] = t[j]; }
+            for (uint32_t k = warp; k < nch; k += nwarps) {
+                const uint64_t s = sync_s[k], e = sync_s[k + 1];
+                if (s < e) rle_range(p, data, s, e, dst + len + size_s[k]); /* into the free tail of the slot */
             }
-            if (lane == 0) {
+            __syncthreads();
+            /* down over the data: the output is shorter than the data, so the two ranges do not overlap */
+            for (uint64_t k = tid; k < rsz; k += RLE_THREADS) dst[hdr + k] = dst[len + k];
+            if (tid == 0) {
                 dst[10] = (uint8_t)a.rle_mode;
                 a.sizes[tile] = hdr + rsz;
             }
@@ -1235,13 +1358,13 @@ __global__ void __launch_bounds__(128) rle_kernel(const __grid_constant__ EncArg
     if (a.raw_size <= len) { /* stored fallback, reference: QB3encode.cpp:461-485 */
         const uint32_t ts = a.raw_size / ((uint64_t)a.w * a.h * a.bands);
         const uint64_t line = (uint64_t)a.w * a.bands * ts, pitch = a.stride * ts;
-        __syncwarp();
-        for (uint32_t i = lane; i < a.hdr_stored_len; i += 32) dst[i] = a.hdr_stored[i];
-        for (uint64_t i = lane; i < a.raw_size; i += 32) {
+        __syncthreads();
+        for (uint32_t i = tid; i < a.hdr_stored_len; i += RLE_THREADS) dst[i] = a.hdr_stored[i];
+        for (uint64_t i = tid; i < a.raw_size; i += RLE_THREADS) {
             const uint64_t y = i / line, x = i - y * line;
             dst[a.hdr_stored_len + i] = src[y * pitch + x];
         }
-        if (lane == 0) a.sizes[tile] = a.hdr_stored_len + a.raw_size;
+        if (tid == 0) a.sizes[tile] = a.hdr_stored_len + a.raw_size;
     }
 }
 
@@ -1335,12 +1458,19 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
     if (err != cudaSuccess) return err;
     kern<<<(unsigned)(ntiles * (a.parts > 1 ? a.parts : 1)), threads, smem, st>>>(a);
     err = cudaGetLastError();
+    if (err == cudaSuccess && a.parts > 1 && best) { /* EncArgs::best_pass */
+        best_resolve_kernel<<<(unsigned)ntiles, 256, 0, st>>>(a);
+        EncArgs b = a;
+        b.best_pass = 2;
+        kern<<<(unsigned)(ntiles * a.parts), threads, smem, st>>>(b);
+        err = cudaGetLastError();
+    }
     if (err == cudaSuccess && a.parts > 1) {
         stitch_kernel<<<dim3(a.parts, (unsigned)ntiles), 256, 0, st>>>(a, (uint32_t)sizeof(T));
         err = cudaGetLastError();
     }
     if (err != cudaSuccess || !a.rle_mode) return err;
-    rle_kernel<<<(unsigned)((ntiles + 3) / 4), 128, 0, st>>>(a, (uint32_t)ntiles);
+    rle_kernel<<<(unsigned)ntiles, RLE_THREADS, 0, st>>>(a, (uint32_t)ntiles);
     return cudaGetLastError();
 }
 

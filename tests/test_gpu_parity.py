@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import qb3_b200 as q
-from helpers import (CONTENT_KINDS, DTYPES, MODE_BASE, MODE_BEST, MODE_FTL, PRODUCT_SO, REF_SO, QB3Lib, content, dtype_code,
+from helpers import (CONTENT_KINDS, DTYPES, MODE_BASE, MODE_BEST, MODE_CF, MODE_CF_H, MODE_FTL, MODE_RLE, MODE_RLE_H, PRODUCT_SO, REF_SO, QB3Lib, content, dtype_code,
                      golden_cases, golden_check_stream, golden_image, golden_kwargs, have_ref, oracle, synth_tiles)
 
 pytestmark = pytest.mark.gpu
@@ -497,6 +497,108 @@ def test_batch_large_tiles_in_parts_match_oracle(shape, dt, kw):
     cfg2, dst2, sizes2, _ = encode_tiles(noise, mode=MODE_BASE)
     want = oracle().encode(noise[0], mode=MODE_BASE)
     assert dst2.cpu().numpy()[0, :int(sizes2[0])].tobytes() == want and want[10] == 255
+
+
+def _best_parts_content(kind, w, h, b, dt):
+    """Content whose BEST coding leans on the band's last written factor across the parts of a tile."""
+    base = synth_tiles(1, w, h, b, np.uint8)[0].astype(np.uint64)
+    yy = np.arange(h, dtype=np.uint64)[:, None, None]
+    if kind == "synth":
+        v = synth_tiles(1, w, h, b, dt)[0]
+        return v
+    if kind == "cf5":            # one factor everywhere: every part starts by meeting the factor that comes in
+        v = base * np.uint64(5)
+    elif kind == "cfbands":      # the factor changes every 40 rows, out of step with the parts
+        f = np.array([5, 5, 3, 7, 5, 2, 2, 9, 3, 3], dtype=np.uint64)[(yy // np.uint64(40)) % np.uint64(10)]
+        v = (base >> np.uint64(2)) * f
+    elif kind == "cfrare":       # plain data with a stripe of factor 6 now and then (most parts never meet a factor)
+        v = base.copy()
+        stripe = ((yy // np.uint64(4)) % np.uint64(37)) == 0
+        v = np.where(stripe, (base >> np.uint64(3)) * np.uint64(6), v)
+    elif kind == "fewcf":        # few distinct values, all multiples of 3: index groups compete with factor groups
+        rng = np.random.default_rng(11)
+        pal = np.array([0, 3, 6, 30, 33, 96], dtype=np.uint64)
+        v = pal[rng.integers(0, 6, size=(h, w, b))]
+        v[h // 3: h // 3 + 50] = pal[rng.integers(0, 6, size=(50, w, b))] * np.uint64(2)
+    else:
+        raise ValueError(kind)
+    dt = np.dtype(dt)
+    udt = np.dtype("uint%d" % (8 * dt.itemsize))
+    return np.ascontiguousarray(v.astype(udt)).view(dt)
+
+
+@pytest.mark.parametrize("kind,shape,dt,kw", [
+    ("synth", (1024, 1024, 3), np.uint8, dict(mode=MODE_BEST)),
+    ("cf5", (512, 768, 3), np.uint8, dict(mode=MODE_BEST)),
+    ("cf5", (260, 517, 2), np.uint16, dict(mode=MODE_CF_H, cband=[1, 1])),
+    ("cfbands", (512, 1024, 3), np.uint8, dict(mode=MODE_BEST)),
+    ("cfbands", (300, 1000, 1), np.int16, dict(mode=MODE_CF)),
+    ("cfrare", (512, 2048, 3), np.uint8, dict(mode=MODE_BEST)),
+    ("fewcf", (256, 1536, 2), np.uint8, dict(mode=MODE_BEST)),
+    ("cfbands", (128, 1024, 1), np.uint32, dict(mode=MODE_BEST)),
+    ("cf5", (64, 640, 1), np.uint64, dict(mode=MODE_BEST)),
+])
+def test_best_tiles_in_parts_match_oracle(kind, shape, dt, kw):
+    """BEST on few large tiles: parts coded without knowing the band's last written factor, the factors handed down by
+    best_resolve_kernel, dependent parts coded again (EncArgs::best_pass), RLE by chunks afterwards: byte identical
+    to the oracle, decodable, and the running state that comes back is the oracle's."""
+    torch = torch_mod()
+    w, h, b = shape
+    tiles = np.stack([_best_parts_content(kind, w, h, b, dt), _best_parts_content("synth", w, h, b, dt)])
+    cfg, dst, sizes, status = encode_tiles(tiles, **kw)
+    sz, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
+    for t in range(2):
+        want = oracle().encode(tiles[t], **kw)
+        assert int(sz[t]) == len(want) and dst_h[t, :sz[t]].tobytes() == want, "tile %d differs from the oracle" % t
+    offsets = torch.arange(2, device="cuda", dtype=torch.int64) * dst.stride(0)
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, 2)
+    torch.cuda.synchronize()
+    assert not st.cpu().numpy().any()
+    assert np.array_equal(out.cpu().numpy().view(dt).reshape(tiles.shape), tiles)
+
+
+@pytest.mark.parametrize("kind,shape,dt,mode", [
+    ("zeros", (512, 512, 3), np.uint8, MODE_BEST),        # one long run of zero bytes
+    ("lownoise", (512, 512, 1), np.uint8, MODE_BEST),     # rungs 0..2: streams full of 00 and FF bytes
+    ("lownoise", (700, 300, 2), np.uint16, MODE_RLE_H),
+    ("steps", (512, 512, 3), np.uint8, MODE_BEST),
+    ("halfzero", (1024, 512, 1), np.uint8, MODE_BEST),    # runs that start and end inside chunks
+    ("halfzero", (2048, 2048, 1), np.uint8, MODE_RLE),    # in parts, then RLE
+    ("ffpairs", (512, 256, 1), np.uint8, MODE_BEST),
+])
+def test_rle_by_chunks_matches_oracle(kind, shape, dt, mode):
+    """rle_kernel cuts a stream into chunks at bytes that are neither 00 nor FF and codes them independently: the bytes
+    must be the serial transducer's (QB3encode.cpp:271-332), whatever falls on a chunk boundary."""
+    torch = torch_mod()
+    w, h, b = shape
+    if kind == "halfzero":
+        rng = np.random.default_rng(5)
+        v = rng.integers(0, 3, size=(h, w, b)).astype(dt)
+        v[:, : w // 2] = 0
+        v[h // 3: h // 3 + 64] = 0
+        v[::17, ::5] = 7
+    elif kind == "ffpairs":   # top half: every value four less than the one before it in coding order, which codes as
+        v = np.zeros((h, w, b), dtype=dt)          # runs of one bits (thousands of FF FF pairs); bottom half: zeros
+        cur = 0
+        for by in range(h // 8):
+            for bx in range(w // 4):
+                for i in range(16):
+                    n = (0x01548cd9aefb7623 >> (4 * (15 - i))) & 15
+                    cur = (cur - 4) & 255
+                    v[4 * by + (n >> 2), 4 * bx + (n & 3), 0] = cur
+    else:
+        v = content(kind, w, h, b, dt)
+    tiles = np.stack([v, v[::-1].copy()])
+    cfg, dst, sizes, status = encode_tiles(tiles, mode=mode)
+    sz, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
+    for t in range(2):
+        want = oracle().encode(tiles[t], mode=mode)
+        assert int(sz[t]) == len(want) and dst_h[t, :sz[t]].tobytes() == want, "tile %d differs from the oracle (mode byte %d)" % (t, want[10])
+    offsets = torch.arange(2, device="cuda", dtype=torch.int64) * dst.stride(0)
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, 2)
+    torch.cuda.synchronize()
+    assert not st.cpu().numpy().any()
+    assert np.array_equal(out.cpu().numpy().view(dt).reshape(tiles.shape), tiles)
 
 
 @pytest.mark.parametrize("dt,mode", [(np.uint8, MODE_BASE), (np.uint8, MODE_BEST), (np.uint16, MODE_BEST), (np.int32, MODE_BASE),

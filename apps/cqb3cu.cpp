@@ -324,8 +324,9 @@ static void fill_config(const Options &opt, const Image &im, const string &mappi
     }
 }
 
-/* -m x: the ten RGB band maps of cqb3.cpp:567-570 on the device at once. The image goes up once; every map is encoded
-   on its own stream into its own slot; only the sizes and then the smallest stream come back. */
+/* -m x: the ten RGB band maps of cqb3.cpp:567-570 on the device. The image goes up once; every map is only measured
+   (qb3cu_encoded_size_batch: the encode kernel without its packing, no destination), each on a stream of its own;
+   the first of the smallest is then encoded for real and only that stream comes back. */
 static int encode_bandmix(const Options &opt, Image im, vector<uint8_t> &dest, double &seconds)
 {
     static const char *combos[10] = {"1,1,1", "0,0,0", "0,0,2", "0,1,0", "0,1,1", "0,1,2", "0,2,2", "1,1,2", "2,1,2", "2,2,2"};
@@ -334,15 +335,15 @@ static int encode_bandmix(const Options &opt, Image im, vector<uint8_t> &dest, d
     for (int k = 0; k < 10; k++) { fill_config(opt, im, combos[k], cfg[k]); cfg[k].stride = stride; }
     const size_t slot = qb3cu_slot_bytes(&cfg[0]), extent = ((im.h - 1) * stride + im.w * im.bands) * ts;
     uint8_t *d_src = nullptr, *d_dst = nullptr;
-    uint64_t *d_sizes = nullptr, sizes[10];
+    uint64_t *d_sizes = nullptr, sizes[11];
     cudaStream_t st[10];
-    if (cudaMalloc(&d_src, extent) || cudaMalloc(&d_dst, 10 * slot) || cudaMalloc(&d_sizes, 80)) { cerr << "No device memory\n"; return 2; }
+    if (cudaMalloc(&d_src, extent) || cudaMalloc(&d_dst, slot) || cudaMalloc(&d_sizes, 88)) { cerr << "No device memory\n"; return 2; }
     const auto t1 = chrono::high_resolution_clock::now();
     cudaMemcpy(d_src, im.px.data() + offset, extent, cudaMemcpyHostToDevice);
     int rc = 0;
     for (int k = 0; k < 10; k++) {
         cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking);
-        rc |= qb3cu_encode_batch(&cfg[k], d_src, extent, d_dst + k * slot, slot, d_sizes + k, nullptr, nullptr, 1, st[k]);
+        rc |= qb3cu_encoded_size_batch(&cfg[k], d_src, extent, d_sizes + k, 1, st[k]);
     }
     for (int k = 0; k < 10; k++) { cudaStreamSynchronize(st[k]); cudaStreamDestroy(st[k]); }
     cudaMemcpy(sizes, d_sizes, 80, cudaMemcpyDeviceToHost);
@@ -351,9 +352,12 @@ static int encode_bandmix(const Options &opt, Image im, vector<uint8_t> &dest, d
         if (opt.verbose && (k == 0 || sizes[k] < sizes[best])) cout << "Band mix " << combos[k] << ", size " << sizes[k] << endl;
         if (sizes[k] < sizes[best]) best = k;
     }
+    if (!rc) rc = qb3cu_encode_batch(&cfg[best], d_src, extent, d_dst, slot, d_sizes + 10, nullptr, nullptr, 1, nullptr);
     if (!rc) {
-        dest.resize(sizes[best]);
-        cudaMemcpy(dest.data(), d_dst + best * slot, sizes[best], cudaMemcpyDeviceToHost);
+        cudaMemcpy(sizes + 10, d_sizes + 10, 8, cudaMemcpyDeviceToHost);
+        if (sizes[10] != sizes[best]) { cerr << "Size pass and encode disagree\n"; rc = 2; }
+        dest.resize(sizes[10]);
+        cudaMemcpy(dest.data(), d_dst, sizes[10], cudaMemcpyDeviceToHost);
     }
     seconds += chrono::duration<double>(chrono::high_resolution_clock::now() - t1).count();
     cudaFree(d_src); cudaFree(d_dst); cudaFree(d_sizes);

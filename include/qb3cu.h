@@ -91,6 +91,16 @@ LIBQB3_EXPORT int qb3cu_encode_batch(const qb3cu_config *cfg, const void *d_src,
                                      uint64_t *d_state, size_t ntiles, void *stream);
 
 /*
+ * The sizes qb3cu_encode_batch would report, without the streams: d_sizes[t] = bytes of tile t's stream (stored
+ * fallback included). Replaces the encodes a caller runs only to compare sizes -- cqb3 -m x tries ten band maps and
+ * keeps the smallest (cqb3.cpp:561-586). The encode kernel runs with its packing and stores left out and needs no
+ * destination; with an RLE mode (2, 3, 6, 7) the streams have to exist for the byte pass to be measured, so they are
+ * made in scratch memory of the library's own.
+ */
+LIBQB3_EXPORT int qb3cu_encoded_size_batch(const qb3cu_config *cfg, const void *d_src, size_t src_tile_pitch,
+                                           uint64_t *d_sizes, size_t ntiles, void *stream);
+
+/*
  * Decodes ntiles streams whose headers must all describe width x height x bands of dtype (mode, quanta,
  * order and cband are read from each stream's own header, cfg->stride is the output stride). cfg->mode is
  * only a hint: when it names an RLE mode (2, 3, 6, 7 -- QB3M_BEST is 7), room is set aside to expand RLE

@@ -52,6 +52,8 @@ def lib():
         L.qb3cu_slot_bytes.restype, L.qb3cu_slot_bytes.argtypes = sz, [cfgp]
         L.qb3cu_encode_batch.restype = C.c_int
         L.qb3cu_encode_batch.argtypes = [cfgp, vp, sz, vp, sz, u64p, u32p, u64p, sz, vp]
+        L.qb3cu_encoded_size_batch.restype = C.c_int
+        L.qb3cu_encoded_size_batch.argtypes = [cfgp, vp, sz, u64p, sz, vp]
         L.qb3cu_decode_batch.restype = C.c_int
         L.qb3cu_decode_batch.argtypes = [cfgp, vp, u64p, u64p, vp, sz, u32p, C.c_int, sz, vp]
         L.qb3cu_pack_streams.restype = C.c_int
@@ -136,6 +138,19 @@ def encode_batch(cfg, src, ntiles, dst=None, sizes=None, status=None, state=None
                                   ntiles, _stream_handle(stream))
     _check(rc, "qb3cu_encode_batch")
     return dst, sizes, status
+
+
+def encoded_size_batch(cfg, src, ntiles, sizes=None, tile_pitch=None, stream=None):
+    """The stream sizes encode_batch would report, without making the streams (qb3cu_encoded_size_batch)."""
+    import torch
+    if tile_pitch is None:
+        tile_pitch = cfg.width * cfg.height * cfg.bands * TYPESIZE[cfg.dtype] if not cfg.stride else \
+            cfg.stride * cfg.height * TYPESIZE[cfg.dtype]
+    if sizes is None:
+        sizes = torch.empty((ntiles,), dtype=torch.int64, device=src.device)
+    rc = lib().qb3cu_encoded_size_batch(C.byref(cfg), src.data_ptr(), tile_pitch, sizes.data_ptr(), ntiles, _stream_handle(stream))
+    _check(rc, "qb3cu_encoded_size_batch")
+    return sizes
 
 
 def decode_batch(cfg, streams, offsets, lens, ntiles, out=None, status=None, ref_compat=False, tile_pitch=None,

@@ -750,10 +750,19 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
     pl.sel_or = 0x4440;
     pl.bpi = bands <= 32 ? 32 / bands : 1;
     pl.gpi = bands <= 32 ? pl.bpi * bands : 32;
-    auto whole = [&](uint32_t ub) { return bands <= 32 ? (ub + pl.bpi - 1) / pl.bpi * pl.bpi : ub; };
+    /* a unit is whole rebuild iterations, and its rows whole 16 byte units so that they leave as 16 byte vectors */
+    uint32_t step = 1;
+    {
+        uint32_t unit = 16;
+        const uint32_t bb = 4 * bands * (uint32_t)sizeof(T);
+        while (bb % unit) unit >>= 1;
+        const uint32_t al = 16 / unit, it = bands <= 32 ? pl.bpi : 1;
+        step = it;
+        while (step % al) step += it; /* least common multiple */
+    }
+    auto whole = [&](uint32_t ub) { return (ub + step - 1) / step * step; };
     uint32_t ub = 128 / bands;
-    if (ub < 1) ub = 1;
-    ub = whole(ub);
+    ub = ub < step ? step : ub / step * step;
     if (ub > nbx) ub = nbx;
     pl.upr = (nbx + ub - 1) / ub;
     pl.ub = whole((nbx + pl.upr - 1) / pl.upr); /* the block row cut evenly */

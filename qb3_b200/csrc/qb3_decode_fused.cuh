@@ -489,7 +489,8 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
     /* ==================================================================== rebuild warps */
     /* The scanner keeps its warp scheduler to itself: the warps that would share it (same warp id modulo 4) leave, the
        others are numbered 0 .. rwarps - 1. Whatever a rebuild warp issues there is taken from the one warp the whole
-       CTA waits for. */
+       CTA waits for. (Letting those two rebuild as well when a CTA has 28 streams and the rebuild is what it waits
+       for was measured: 10.7 -> 11.3 ms for 4096 tiles, the scanner loses more than the rebuild gains.) */
     if ((warp & 3) == (scan_warp & 3)) return;
     const uint32_t rw = warp - (warp + 3 - (scan_warp & 3)) / 4 - (warp > feed_warp ? 1 : 0), FULL = 0xffffffffu;
     const uint32_t rowpitch = pl.rowpitch, rowelems = rowpitch / (uint32_t)sizeof(T);
@@ -497,6 +498,14 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
     const bool small_bands = bands <= 32;
     const uint32_t lb = small_bands ? lane / bands : 0, lc = small_bands ? lane - lb * bands : 0;
     const bool is_signed = a.dtype & 1;
+    uint32_t poff[16]; /* where the 16 values of a block go in the staged rows, by the stream's scan curve */
+    uint64_t poff_order = HILBERT;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t n = (uint32_t)(HILBERT >> (4 * (15 - i))) & 15;
+        poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
+    }
+    const uint32_t c4440r = pl.sel_or;
 
     for (uint32_t u = 0; u < nunits; u++) {
         const uint32_t slot = u % pl.nu, by = u / pl.upr, j = u - by * pl.upr;
@@ -511,20 +520,22 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
             const uint8_t *cb = cbs + s * bands;
             const bool ftl = fs.flags & FS_FTL, derived = fs.flags & FS_DERIVED, sweep = fs.flags & FS_SWEEP;
             const uint64_t quanta = fs.quanta;
-            uint32_t poff[16]; /* where the 16 values of a block go in the staged rows */
+            if (fs.order != poff_order) { /* hardly ever: the streams of a batch come from one encoder */
+                poff_order = fs.order;
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t n = (uint32_t)(fs.order >> (4 * (15 - i))) & 15;
-                poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t n = (uint32_t)(fs.order >> (4 * (15 - i))) & 15;
+                    poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
+                }
             }
             W carry = small_bands && lane < pl.gpi ? prevS[s * bands + lc] : (W)0;
             W *pcfc = pcfS + s * bands;
 
-            for (uint32_t it0 = 0; it0 < ng; it0 += pl.gpi) {
+            for (uint32_t it0 = 0, blk0 = 0; it0 < ng; it0 += pl.gpi, blk0 += pl.bpi) {
                 const uint32_t g = it0 + lane;
                 const bool active = lane < pl.gpi && g < ng;
                 uint32_t blk, c;
-                if (small_bands) { blk = it0 / bands + lb; c = lc; }
+                if (small_bands) { blk = blk0 + lb; c = lc; }
                 else { blk = g / bands; c = g - blk * bands; }
                 const uint32_t core = active ? cb[c] : c;
 
@@ -569,18 +580,19 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                                 /* 16 bit data: arithmetic (QB3decode.h:119-129), then the middle swap of rungs 1..7 */
                                 const uint32_t fm1 = 2 * half - 1, sm = r < 8 ? 4 * half - 1 : 0;
                                 uint32_t z = x >> swl, used = swl;
-                                auto take = [&](const int i) {
-                                    const uint32_t len = __byte_perm(lens, 0u, (z & 3) | 0x4440);
+                                auto take = [&](const int i, auto step_tag) {
+                                    constexpr bool STEP = decltype(step_tag)::value;
+                                    const uint32_t len = __byte_perm(lens, 0u, (z & 3) | c4440r);
                                     if (BITS == 8) {
                                         const uint32_t ta = (z & cmask) | gb;
                                         d[i] = lds_s8(ta);
-                                        if (!ftl) M += lds_u8(ta + 1024) << i;
+                                        if (STEP) M += lds_u8(ta + 1024) << i;
                                     }
                                     else {
                                         const uint32_t shv = __byte_perm(0x02010201u, 0u, (z & 3) | 0x4440);
                                         uint32_t val = ((z & ((1u << len) - 1)) >> shv) + half * (len - r);
                                         if (val - fm1 <= 1u) val ^= sm;
-                                        if (!ftl) M += ((val >> r) & 1) << i;
+                                        if (STEP) M += ((val >> r) & 1) << i;
                                         d[i] = (SW)((val >> 1) ^ (0u - (val & 1)));
                                     }
                                     z >>= len;
@@ -597,22 +609,28 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                                     z = wv[0];
                                     used = 0;
                                 };
-                                if (BITS == 16 && r == 15) { /* two 17 bit codes do not fit a window; rare */
-                                    shift_window(16);
-#pragma unroll
-                                    for (int i = 0; i < 16; i++) { take(i); shift_window(15 - i); }
-                                }
-                                else {
-#pragma unroll
-                                    for (int i = 0; i < NV0; i++) take(i);
-                                    shift_window(16 - NV0);
-#pragma unroll
-                                    for (int i0 = NV0; i0 < 16; i0 += VPB) {
-#pragma unroll
-                                        for (int i = i0; i < i0 + VPB && i < 16; i++) take(i);
-                                        if (i0 + VPB < 16) shift_window(16 - i0 - VPB);
+                                /* FTL streams have no step coding: their build of the sixteen values leaves the rung bits alone
+                                   (a warp works on one stream, so the branch is uniform) */
+                                auto values = [&](auto step_tag) {
+                                    if (BITS == 16 && r == 15) { /* two 17 bit codes do not fit a window; rare */
+                                        shift_window(16);
+    #pragma unroll
+                                        for (int i = 0; i < 16; i++) { take(i, step_tag); shift_window(15 - i); }
                                     }
-                                }
+                                    else {
+    #pragma unroll
+                                        for (int i = 0; i < NV0; i++) take(i, step_tag);
+                                        shift_window(16 - NV0);
+    #pragma unroll
+                                        for (int i0 = NV0; i0 < 16; i0 += VPB) {
+    #pragma unroll
+                                            for (int i = i0; i < i0 + VPB && i < 16; i++) take(i, step_tag);
+                                            if (i0 + VPB < 16) shift_window(16 - i0 - VPB);
+                                        }
+                                    }
+                                };
+                                if (ftl) values(std::false_type());
+                                else values(std::true_type());
                                 if (!ftl) { /* step undo (QB3decode.h:285-289) on the unfolded value: bit r set in a value
                                                moves an even one up by 2^(r-1) and an odd one down */
                                     const int kk = step_decode_index(M);

@@ -499,6 +499,32 @@ def test_batch_large_tiles_in_parts_match_oracle(shape, dt, kw):
     assert dst2.cpu().numpy()[0, :int(sizes2[0])].tobytes() == want and want[10] == 255
 
 
+@pytest.mark.parametrize("shape,dt,kw", [
+    ((6, 512, 512, 3), np.uint8, dict(mode=MODE_FTL)),
+    ((3, 300, 200, 4), np.uint16, dict(mode=MODE_BASE, cband=[1, 1, 1, 3])),
+    ((3, 128, 128, 1), np.int32, dict(mode=MODE_CF_H, quanta=5)),
+    ((2, 256, 256, 3), np.uint8, dict(mode=MODE_BEST)),            # RLE mode: measured on streams made in scratch
+    ((1, 1024, 2048, 3), np.uint8, dict(mode=MODE_BASE)),          # one large tile: in parts
+    ((1, 1024, 1024, 1), np.uint16, dict(mode=MODE_CF_H)),         # BEST without RLE, in parts
+    ((4, 3, 50, 2), np.uint8, dict(mode=MODE_FTL)),                # narrow images go through the reorder
+])
+def test_size_only_pass_matches_encode(shape, dt, kw):
+    """qb3cu_encoded_size_batch (the pass behind cqb3cu -m x, cqb3.cpp:561-586): the sizes of the streams without the
+    streams -- equal to what the encode reports and to the oracle's stream lengths, stored fallback included."""
+    torch = torch_mod()
+    n, w, h, b = shape
+    tiles = synth_tiles(n, w, h, b, dt)
+    tiles[n - 1] = np.random.default_rng(9).integers(0, 1 << 8 * np.dtype(dt).itemsize, tiles[0].shape).astype(np.uint64).astype(tiles.dtype) \
+        if np.dtype(dt).kind == "u" else tiles[n - 1]     # noise: stored
+    cfg, dst, sizes, status = encode_tiles(tiles, **kw)
+    src = torch.from_numpy(tiles.view(np.uint8).reshape(n, -1)).cuda()
+    only = q.encoded_size_batch(cfg, src, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(only.cpu().numpy(), sizes.cpu().numpy())
+    for t in (0, n - 1):
+        assert int(only[t]) == len(oracle().encode(tiles[t], **kw))
+
+
 def _best_parts_content(kind, w, h, b, dt):
     """Content whose BEST coding leans on the band's last written factor across the parts of a tile."""
     base = synth_tiles(1, w, h, b, np.uint8)[0].astype(np.uint64)

@@ -1368,6 +1368,137 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant_
     }
 }
 
+/*
+ * The same for few, large tiles: a CTA would walk tens of megabytes alone (19 streams of 27 MB took 32 ms), so S CTAs share
+ * a tile and the steps of rle_kernel become launches: 0 measures the chunks, 1 (one CTA per tile) places them and
+ * decides, 2 writes them into the free tail of the slot, 3 moves them down or stores the tile. What the later steps
+ * need to know about a tile is settled in step 1 (RleWide::meta), for the last step changes the tile's size and mode
+ * byte while its other CTAs are still at work.
+ */
+struct RleWide {
+    uint32_t *sync;             /* [tile][RLE_MAXCHUNKS + 1] chunk starts */
+    uint32_t *size;             /* [tile][RLE_MAXCHUNKS] chunk sizes, then their places in the output */
+    unsigned long long *meta;   /* [tile][4]: what to do (0 nothing, 1 RLE, 2 store), stream length, RLE size, unused */
+    uint32_t S;
+};
+__device__ static uint64_t rle_chunk_size(uint64_t data, uint32_t &nch)
+{
+    uint64_t csize = 1024; /* chunks of at least 1 KB, at most RLE_MAXCHUNKS of them */
+    while ((data + csize - 1) / csize > RLE_MAXCHUNKS) csize *= 2;
+    nch = (uint32_t)((data + csize - 1) / csize);
+    return csize;
+}
+__global__ void __launch_bounds__(RLE_THREADS) rle_wide_kernel(const __grid_constant__ EncArgs a, const RleWide w, uint32_t phase)
+{
+    __shared__ uint32_t scratch[36];
+    const uint32_t tile = blockIdx.y, part = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RLE_THREADS / 32;
+    uint8_t *dst = a.dst + (uint64_t)tile * a.slot;
+    const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
+    const uint64_t hdr = a.hdr_len;
+    uint32_t *sync_g = w.sync + (uint64_t)tile * (RLE_MAXCHUNKS + 1), *size_g = w.size + (uint64_t)tile * RLE_MAXCHUNKS;
+    unsigned long long *meta = w.meta + 4 * (uint64_t)tile;
+    if (phase <= 1) {
+        const uint64_t len = a.sizes[tile], data = len - hdr;
+        const bool stored = dst[10] == M_STORED, try_rle = !stored && len <= a.max_size / 2 && data < 0xffffffffull;
+        uint32_t nch = 0;
+        const uint64_t csize = try_rle ? rle_chunk_size(data, nch) : 0;
+        const uint8_t *p = dst + hdr;
+        if (phase == 0) {
+            const uint32_t per = (nch + w.S - 1) / w.S, k1 = min(nch, (part + 1) * per);
+            for (uint32_t k = part * per + warp; k < k1; k += nwarps) {
+                const uint64_t s = rle_sync(p, data, k * csize), e = k + 1 < nch ? rle_sync(p, data, (k + 1) * csize) : data;
+                const uint64_t z = s < e ? rle_range(p, data, s, e, nullptr) : 0;
+                if (lane == 0) { sync_g[k] = (uint32_t)s; size_g[k] = (uint32_t)z; }
+            }
+            return;
+        }
+        uint64_t rsz = 0; /* phase 1: the chunks' places, and what becomes of the tile */
+        for (uint32_t k0 = 0; k0 < nch; k0 += RLE_THREADS) {
+            const uint32_t k = k0 + tid, v = k < nch ? size_g[k] : 0u;
+            uint32_t total;
+            const uint32_t off = block_exclusive_scan(v, scratch, total);
+            __syncthreads();
+            if (k < nch) size_g[k] = (uint32_t)rsz + off;
+            rsz += total;
+        }
+        if (tid == 0) {
+            sync_g[nch] = (uint32_t)data;
+            const bool rle = try_rle && rsz <= a.max_size - len && rsz < data;
+            meta[0] = rle ? 1 : (!stored && a.raw_size <= len) ? 2 : 0;
+            meta[1] = len;
+            meta[2] = rsz;
+        }
+        return;
+    }
+    const uint64_t what = meta[0], len = meta[1], rsz = meta[2], data = len - hdr;
+    if (phase == 2) {
+        if (what != 1) return;
+        uint32_t nch = 0;
+        rle_chunk_size(data, nch);
+        const uint32_t per = (nch + w.S - 1) / w.S, k1 = min(nch, (part + 1) * per);
+        for (uint32_t k = part * per + warp; k < k1; k += nwarps) {
+            const uint64_t s = sync_g[k], e = sync_g[k + 1];
+            if (s < e) rle_range(dst + hdr, data, s, e, dst + len + size_g[k]);
+        }
+        return;
+    }
+    if (what == 1) { /* down over the data: the output is shorter than the data, so the two ranges do not overlap */
+        const uint64_t per = (rsz + w.S - 1) / w.S, lo = per * part, hi = min(rsz, lo + per);
+        for (uint64_t k = lo + tid; k < hi; k += RLE_THREADS) dst[hdr + k] = dst[len + k];
+        if (part == 0 && tid == 0) {
+            dst[10] = (uint8_t)a.rle_mode;
+            a.sizes[tile] = hdr + rsz;
+        }
+    }
+    else if (what == 2) { /* stored fallback, reference: QB3encode.cpp:461-485 */
+        const uint32_t ts = a.raw_size / ((uint64_t)a.w * a.h * a.bands);
+        const uint64_t line = (uint64_t)a.w * a.bands * ts, pitch = a.stride * ts;
+        const uint64_t per = (a.raw_size + w.S - 1) / w.S, lo = per * part, hi = min(a.raw_size, lo + per);
+        if (part == 0)
+            for (uint32_t i = tid; i < a.hdr_stored_len; i += RLE_THREADS) dst[i] = a.hdr_stored[i];
+        for (uint64_t i = lo + tid; i < hi; i += RLE_THREADS) {
+            const uint64_t y = i / line, x = i - y * line;
+            dst[a.hdr_stored_len + i] = src[y * pitch + x];
+        }
+        if (part == 0 && tid == 0) a.sizes[tile] = a.hdr_stored_len + a.raw_size;
+    }
+}
+
+cudaMemPool_t scratch_pool(); /* qb3_decode.cu */
+void count_launches(uint64_t n); /* qb3_cabi.cu */
+
+/* the RLE pass of a batch: one CTA per tile, or for few tiles several (rle_wide_kernel) */
+static cudaError_t launch_rle(const EncArgs &a, size_t ntiles, cudaStream_t st)
+{
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    /* streams of less than 64 KB are a handful of chunks: nothing to share */
+    if (ntiles >= (size_t)2 * nsm || a.max_size / 2 < 65536) {
+        rle_kernel<<<(unsigned)ntiles, RLE_THREADS, 0, st>>>(a, (uint32_t)ntiles);
+        return cudaGetLastError();
+    }
+    RleWide w;
+    w.S = (uint32_t)(((size_t)4 * nsm + ntiles - 1) / ntiles);
+    if (w.S > 128) w.S = 128;
+    const size_t sync_bytes = ntiles * (RLE_MAXCHUNKS + 1) * 4, size_bytes = ntiles * RLE_MAXCHUNKS * 4;
+    uint8_t *tmp = nullptr;
+    cudaMemPool_t pool = scratch_pool();
+    const size_t bytes = ((sync_bytes + size_bytes + 15) & ~(size_t)15) + ntiles * 32;
+    cudaError_t err = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void **>(&tmp), bytes, pool, st)
+                           : cudaMallocAsync(reinterpret_cast<void **>(&tmp), bytes, st);
+    if (err != cudaSuccess) return err;
+    w.sync = reinterpret_cast<uint32_t *>(tmp);
+    w.size = reinterpret_cast<uint32_t *>(tmp + sync_bytes);
+    w.meta = reinterpret_cast<unsigned long long *>(tmp + ((sync_bytes + size_bytes + 15) & ~(size_t)15));
+    for (uint32_t phase = 0; phase < 4 && err == cudaSuccess; phase++) {
+        rle_wide_kernel<<<dim3(phase == 1 ? 1 : w.S, (unsigned)ntiles), RLE_THREADS, 0, st>>>(a, w, phase);
+        err = cudaGetLastError();
+    }
+    const cudaError_t ferr = cudaFreeAsync(tmp, st);
+    if (err == cudaSuccess) count_launches(3); /* the caller counts one launch for the pass */
+    return err != cudaSuccess ? err : ferr;
+}
+
 /* ------------------------------------------------------------------ stream packing */
 
 /* offsets[t] = sum of the 16 byte rounded sizes before t, total[0] = their sum. One CTA; tiles in chunks of blockDim. */
@@ -1470,8 +1601,7 @@ template <typename T> static cudaError_t launch_encode_t(const EncArgs &a, size_
         err = cudaGetLastError();
     }
     if (err != cudaSuccess || !a.rle_mode) return err;
-    rle_kernel<<<(unsigned)ntiles, RLE_THREADS, 0, st>>>(a, (uint32_t)ntiles);
-    return cudaGetLastError();
+    return launch_rle(a, ntiles, st);
 }
 
 cudaError_t launch_encode(const EncArgs &a, uint32_t tsize, size_t ntiles, uint32_t threads, size_t smem, cudaStream_t st)

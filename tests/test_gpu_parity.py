@@ -591,13 +591,14 @@ def test_best_tiles_in_parts_match_oracle(kind, shape, dt, kw):
     ("halfzero", (1024, 512, 1), np.uint8, MODE_BEST),    # runs that start and end inside chunks
     ("halfzero", (2048, 2048, 1), np.uint8, MODE_RLE),    # in parts, then RLE
     ("ffpairs", (512, 256, 1), np.uint8, MODE_BEST),
+    ("many", (256, 256, 1), np.uint8, MODE_BEST),         # a batch: one CTA per tile does all the steps (rle_kernel)
 ])
 def test_rle_by_chunks_matches_oracle(kind, shape, dt, mode):
     """rle_kernel cuts a stream into chunks at bytes that are neither 00 nor FF and codes them independently: the bytes
     must be the serial transducer's (QB3encode.cpp:271-332), whatever falls on a chunk boundary."""
     torch = torch_mod()
     w, h, b = shape
-    if kind == "halfzero":
+    if kind in ("halfzero", "many"):
         rng = np.random.default_rng(5)
         v = rng.integers(0, 3, size=(h, w, b)).astype(dt)
         v[:, : w // 2] = 0
@@ -614,14 +615,16 @@ def test_rle_by_chunks_matches_oracle(kind, shape, dt, mode):
                     v[4 * by + (n >> 2), 4 * bx + (n & 3), 0] = cur
     else:
         v = content(kind, w, h, b, dt)
-    tiles = np.stack([v, v[::-1].copy()])
+    tiles = np.stack([v, v[::-1].copy()] * (160 if kind == "many" else 1))
+    n = len(tiles)
     cfg, dst, sizes, status = encode_tiles(tiles, mode=mode)
     sz, dst_h = sizes.cpu().numpy(), dst.cpu().numpy()
-    for t in range(2):
+    for t in (0, 1, n - 2, n - 1):
         want = oracle().encode(tiles[t], mode=mode)
         assert int(sz[t]) == len(want) and dst_h[t, :sz[t]].tobytes() == want, "tile %d differs from the oracle (mode byte %d)" % (t, want[10])
-    offsets = torch.arange(2, device="cuda", dtype=torch.int64) * dst.stride(0)
-    out, st = q.decode_batch(cfg, dst, offsets, sizes, 2)
+    assert len(set(sz[0::2])) == 1 and len(set(sz[1::2])) == 1
+    offsets = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, n)
     torch.cuda.synchronize()
     assert not st.cpu().numpy().any()
     assert np.array_equal(out.cpu().numpy().view(dt).reshape(tiles.shape), tiles)

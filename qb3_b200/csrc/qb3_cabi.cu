@@ -16,10 +16,8 @@ cudaMemPool_t scratch_pool(); /* qb3_decode.cu: the library's own stream ordered
 cudaError_t launch_pack(const uint8_t *slots, uint64_t slot, const unsigned long long *sizes, uint8_t *packed,
                         unsigned long long *offsets, unsigned long long *total, uint32_t ntiles, cudaStream_t st);
 
-typedef void (*rows_ready_fn)(void *ctx, uint32_t row0, uint32_t row1, cudaStream_t s);
-int decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
-                      void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream,
-                      uint32_t row_chunks, rows_ready_fn rows_ready, void *rows_ctx);
+int decode_batch_shared(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
+                        void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream);
 
 static thread_local int g_last_cuda_error = 0;
 static std::atomic<uint64_t> g_launches(0);
@@ -253,22 +251,13 @@ int qb3cu_encoded_size_batch(const qb3cu_config *cfg, const void *d_src, size_t 
     return rc != QB3CU_OK ? rc : frc;
 }
 
-int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,
-                       const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch, uint32_t *d_status,
-                       int ref_compat, size_t ntiles, void *stream)
-{
-    return qb3::decode_batch_rows(cfg, d_streams, d_offsets, d_lens, d_dst, dst_tile_pitch, d_status, ref_compat, ntiles,
-                                  stream, 0, nullptr, nullptr);
-}
-
 } /* extern "C" */
 
-/* qb3cu_decode_batch with the number of row chunks of the two pass decode chosen by the caller (0 = default) and a
-   hook that is told when image rows are complete (the host pipeline moves them out while the parse goes on) */
-int qb3::decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,
-                           const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch, uint32_t *d_status,
-                           int ref_compat, size_t ntiles, void *stream, uint32_t row_chunks, rows_ready_fn rows_ready,
-                           void *rows_ctx)
+/* shared_sm: the host pipeline's call -- several batches and an encode are in flight beside this one, so the batch is
+   packed onto as few SMs as hold its streams */
+static int decode_impl(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
+                       void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream,
+                       bool shared_sm)
 {
     if (!geometry_ok(cfg) || !d_streams || !d_offsets || !d_lens || !d_dst || !d_status) return QB3CU_ERR_PARAM;
     if (ntiles == 0) return QB3CU_OK;
@@ -289,18 +278,28 @@ int qb3::decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const
     a.w = cfg->width; a.h = cfg->height; a.bands = cfg->bands; a.dtype = cfg->dtype;
     a.ref_compat = ref_compat != 0;
     a.ntiles = (uint32_t)ntiles;
-    a.row_chunks = row_chunks;
     a.rle_hint = rle_requested(cfg->mode);
-    a.shared_sm = rows_ready != nullptr; /* the host pipeline: several batches and an encode in flight beside this one */
-    a.rows_ready = rows_ready;
-    a.rows_ctx = rows_ctx;
+    a.shared_sm = shared_sm;
     uint32_t launches = 0;
     cudaError_t err = launch_decode(a, tsize, static_cast<cudaStream_t>(stream), launches);
     count_launches(launches);
     return note_cuda(err);
 }
 
+int qb3::decode_batch_shared(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
+                             void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream)
+{
+    return decode_impl(cfg, d_streams, d_offsets, d_lens, d_dst, dst_tile_pitch, d_status, ref_compat, ntiles, stream, true);
+}
+
 extern "C" {
+
+int qb3cu_decode_batch(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets,
+                       const uint64_t *d_lens, void *d_dst, size_t dst_tile_pitch, uint32_t *d_status,
+                       int ref_compat, size_t ntiles, void *stream)
+{
+    return decode_impl(cfg, d_streams, d_offsets, d_lens, d_dst, dst_tile_pitch, d_status, ref_compat, ntiles, stream, false);
+}
 
 int qb3cu_pack_streams(const void *d_slots, size_t slot_bytes, const uint64_t *d_sizes, void *d_packed,
                        uint64_t *d_offsets, uint64_t *d_total, size_t ntiles, void *stream)

@@ -81,13 +81,8 @@ struct DecArgs {
     uint32_t w, h, bands, dtype;
     uint32_t ref_compat;
     uint32_t ntiles;
-    uint32_t row_chunks;  /* host side only: row chunks of the two pass decode, 0 = default */
     uint32_t rle_hint;    /* host side only: the caller expects RLE streams (cfg->mode is an RLE mode): expand them first */
-    uint32_t shared_sm;   /* host side only: scans share their SMs with other kernels (many batches in flight at once) */
-    /* host side only: called when the kernel that completes image rows [row0, row1) of every tile has been enqueued
-       on stream s, so that a caller can start moving them out while the rest of the batch is still being parsed */
-    void (*rows_ready)(void *ctx, uint32_t row0, uint32_t row1, cudaStream_t s);
-    void *rows_ctx;
+    uint32_t shared_sm;   /* host side only: the batch shares the device with other kernels (many batches in flight at once) */
 };
 
 /* header fields of one stream, parsed on the device */

@@ -6,11 +6,10 @@
  * stream with its own staging memory:
  *   encode:  pixels up -> qb3cu_encode_batch -> qb3cu_pack_streams -> index (sizes, offsets, total) down;
  *            the host reads the total and brings down exactly the bytes produced, behind the next chunk's upload
- *   decode:  the chunk's span of stream bytes and its index up -> decode -> pixels down. The decode itself is
- *            pipelined over bands of image rows (scan of a band, then its rebuild); each band of rows leaves for the
- *            host as soon as its rebuild is done, on a third stream, while the parse of the rows below goes on
+ *   decode:  the chunk's span of stream bytes and its index up -> qb3cu_decode_batch's kernels, packed onto as few
+ *            SMs as hold the chunk's streams -> pixels down
  * The copy engines serve both directions at once and a chunk's kernels run beside other chunks' copies. The parse of a
- * chunk takes about 17 ms however few tiles it has (one serial walk per stream), so several chunks are kept in flight.
+ * chunk takes about 9 ms however few tiles it has (one serial walk per stream), so several chunks are kept in flight.
  */
 #include <cstdlib>
 #include <cstring>
@@ -21,10 +20,8 @@
 
 namespace qb3 {
 int note_cuda(cudaError_t e);
-typedef void (*rows_ready_fn)(void *ctx, uint32_t row0, uint32_t row1, cudaStream_t s);
-int decode_batch_rows(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
-                      void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream,
-                      uint32_t row_chunks, rows_ready_fn rows_ready, void *rows_ctx);
+int decode_batch_shared(const qb3cu_config *cfg, const void *d_streams, const uint64_t *d_offsets, const uint64_t *d_lens,
+                        void *d_dst, size_t dst_tile_pitch, uint32_t *d_status, int ref_compat, size_t ntiles, void *stream);
 
 static const uint32_t PIPE_TYPESIZE[8] = {1, 1, 2, 2, 4, 4, 8, 8};
 
@@ -47,11 +44,9 @@ struct DevBuf {
 };
 
 /* one chunk in flight */
-constexpr int ROW_EVENTS = 64;
 struct Stage {
-    cudaStream_t st = nullptr, out = nullptr; /* out: decoded rows to the host, beside the kernels */
-    cudaEvent_t index_ready = nullptr, uploaded = nullptr, rows[ROW_EVENTS] = {};
-    int nrows_ev = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t index_ready = nullptr, uploaded = nullptr;
     DevBuf pix, slots, packed, meta;
     uint64_t *h_meta = nullptr; /* pinned: [sizes or lens | offsets | total] then the status words */
     size_t first = 0, n = 0;    /* the tiles it holds */
@@ -95,45 +90,6 @@ static cudaError_t copy_tiles(const qb3cu_pipe *p, void *dst, size_t dpitch, con
     return cudaSuccess;
 }
 
-/* decode: rows [row0, row1) of every tile of a stage are complete once the work enqueued on 'from' so far is done */
-struct RowsOut {
-    const qb3cu_pipe *p;
-    Stage *s;
-    uint8_t *h_dst;      /* the stage's first tile in the caller's buffer */
-    size_t dst_pitch;
-    uint32_t covered;    /* rows [0, covered) have been sent */
-    cudaError_t err;
-};
-
-static void rows_ready(void *ctx, uint32_t row0, uint32_t row1, cudaStream_t from)
-{
-    RowsOut *r = static_cast<RowsOut *>(ctx);
-    const qb3cu_pipe *p = r->p;
-    Stage &s = *r->s;
-    if (r->err != cudaSuccess || row0 > r->covered || s.nrows_ev >= ROW_EVENTS) return; /* what is left goes at the end */
-    cudaEvent_t ev = s.rows[s.nrows_ev++];
-    cudaError_t e = cudaEventRecord(ev, from);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(s.out, ev, 0);
-    const size_t lpitch = p->strided ? (size_t)p->cfg.stride * p->tsize : p->line_bytes;
-    if (e == cudaSuccess && !p->strided)
-        e = cudaMemcpy2DAsync(r->h_dst + row0 * lpitch, r->dst_pitch, s.pix.p + row0 * lpitch, p->dev_pitch,
-                              (row1 - row0) * lpitch, s.n, cudaMemcpyDeviceToHost, s.out);
-    for (size_t t = 0; e == cudaSuccess && p->strided && t < s.n; t++)
-        e = cudaMemcpy2DAsync(r->h_dst + t * r->dst_pitch + row0 * lpitch, lpitch, s.pix.p + t * p->dev_pitch + row0 * lpitch,
-                              lpitch, p->line_bytes, row1 - row0, cudaMemcpyDeviceToHost, s.out);
-    r->err = e;
-    if (row1 > r->covered) r->covered = row1;
-}
-
-/* can this stream's tile be sent row band by row band? Not when it is finished by the kernels that run after the
-   two pass decode: RLE streams and stored tiles (mode byte, doc/QB3.md:228-235) */
-static bool rows_stream_out(const uint8_t *stream, uint64_t len)
-{
-    if (len < 11) return true; /* bad header: nothing of it is defined anyway */
-    const uint8_t m = stream[10];
-    return !(m == 2 || m == 3 || m == 6 || m == 7 || m == 255);
-}
-
 /* the calling thread on the pipe's device for the length of a call (the current device is per thread) */
 struct OnDevice {
     int before = -1;
@@ -147,7 +103,6 @@ static bool drain(qb3cu_pipe *p)
     bool ok = true;
     for (Stage &s : p->stages) {
         if (s.st) ok &= note_cuda(cudaStreamSynchronize(s.st)) == QB3CU_OK;
-        if (s.out) ok &= note_cuda(cudaStreamSynchronize(s.out)) == QB3CU_OK;
         s.busy = false;
     }
     return ok;
@@ -195,12 +150,9 @@ qb3cu_pipe *qb3cu_pipe_create(const qb3cu_config *cfg, size_t chunk_tiles, int d
     bool ok = true;
     for (Stage &s : p->stages) {
         ok = ok && note_cuda(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking)) == QB3CU_OK
-                && note_cuda(cudaStreamCreateWithFlags(&s.out, cudaStreamNonBlocking)) == QB3CU_OK
                 && note_cuda(cudaEventCreateWithFlags(&s.index_ready, cudaEventDisableTiming)) == QB3CU_OK
                 && note_cuda(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming)) == QB3CU_OK
                 && note_cuda(cudaHostAlloc(reinterpret_cast<void **>(&s.h_meta), meta_bytes(p->chunk), cudaHostAllocMapped)) == QB3CU_OK;
-        for (int i = 0; ok && i < ROW_EVENTS; i++)
-            ok = note_cuda(cudaEventCreateWithFlags(&s.rows[i], cudaEventDisableTiming)) == QB3CU_OK;
     }
     if (!ok) { qb3cu_pipe_destroy(p); return nullptr; }
     return p;
@@ -212,10 +164,8 @@ void qb3cu_pipe_destroy(qb3cu_pipe *p)
     OnDevice here(p->device);
     for (Stage &s : p->stages) {
         if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
-        if (s.out) { cudaStreamSynchronize(s.out); cudaStreamDestroy(s.out); }
         if (s.index_ready) cudaEventDestroy(s.index_ready);
         if (s.uploaded) cudaEventDestroy(s.uploaded);
-        for (cudaEvent_t ev : s.rows) if (ev) cudaEventDestroy(ev);
         if (s.h_meta) cudaFreeHost(s.h_meta);
         s.pix.release(); s.slots.release(); s.packed.release(); s.meta.release();
     }
@@ -295,7 +245,7 @@ int qb3cu_pipe_decode(qb3cu_pipe *p, const void *h_streams, const uint64_t *h_of
 
     auto retire = [&](Stage &s) -> int { /* the chunk that used this stage is complete: hand its status words out */
         if (!s.busy) return QB3CU_OK;
-        if (note_cuda(cudaStreamSynchronize(s.st)) != QB3CU_OK || note_cuda(cudaStreamSynchronize(s.out)) != QB3CU_OK)
+        if (note_cuda(cudaStreamSynchronize(s.st)) != QB3CU_OK)
             return QB3CU_ERR_CUDA;
         memcpy(h_status + s.first, status_of(s.h_meta, s.n), s.n * 4);
         s.busy = false;
@@ -309,11 +259,9 @@ int qb3cu_pipe_decode(qb3cu_pipe *p, const void *h_streams, const uint64_t *h_of
         s.n = ntiles - s.first < p->chunk ? ntiles - s.first : p->chunk;
         /* the bytes this chunk's streams span in host memory, from a 16 byte boundary so that alignment carries over */
         uint64_t lo = ~0ull, hi = 0;
-        bool by_rows = true;
         for (size_t k = 0; k < s.n; k++) {
             const uint64_t o = h_offsets[s.first + k], e = o + h_lens[s.first + k];
             if (e < o) rc = QB3CU_ERR_PARAM;
-            else by_rows &= rows_stream_out(static_cast<const uint8_t *>(h_streams) + o, e - o);
             if (o < lo) lo = o;
             if (e > hi) hi = e;
         }
@@ -335,16 +283,10 @@ int qb3cu_pipe_decode(qb3cu_pipe *p, const void *h_streams, const uint64_t *h_of
         if (note_cuda(cudaMemcpyAsync(s.meta.p, s.h_meta, 2 * s.n * 8, cudaMemcpyHostToDevice, s.st)) != QB3CU_OK
             || (hi > lo && note_cuda(cudaMemcpyAsync(s.packed.p, static_cast<const uint8_t *>(h_streams) + lo, hi - lo,
                                                      cudaMemcpyHostToDevice, s.st)) != QB3CU_OK)) { rc = QB3CU_ERR_CUDA; break; }
-        RowsOut ro = {p, &s, static_cast<uint8_t *>(h_dst) + s.first * dst_tile_pitch, dst_tile_pitch, 0, cudaSuccess};
-        s.nrows_ev = 0;
-        rc = decode_batch_rows(&p->dev_cfg, s.packed.p, d_offs, d_lens, s.pix.p, p->dev_pitch, d_status, ref_compat, s.n, s.st,
-                               by_rows ? 0 : 1, by_rows ? rows_ready : nullptr, &ro);
+        rc = decode_batch_shared(&p->dev_cfg, s.packed.p, d_offs, d_lens, s.pix.p, p->dev_pitch, d_status, ref_compat, s.n, s.st);
         if (rc != QB3CU_OK) break;
-        if (note_cuda(ro.err) != QB3CU_OK) { rc = QB3CU_ERR_CUDA; break; }
-        /* whatever did not leave by rows (all of it on the paths that do not report rows) goes now */
-        if (ro.covered < p->cfg.height
-            && note_cuda(copy_tiles(p, static_cast<uint8_t *>(h_dst) + s.first * dst_tile_pitch, dst_tile_pitch, s.pix.p,
-                                    p->dev_pitch, s.n, cudaMemcpyDeviceToHost, s.st)) != QB3CU_OK) { rc = QB3CU_ERR_CUDA; break; }
+        if (note_cuda(copy_tiles(p, static_cast<uint8_t *>(h_dst) + s.first * dst_tile_pitch, dst_tile_pitch, s.pix.p,
+                                 p->dev_pitch, s.n, cudaMemcpyDeviceToHost, s.st)) != QB3CU_OK) { rc = QB3CU_ERR_CUDA; break; }
         if (note_cuda(cudaMemcpyAsync(status_of(s.h_meta, s.n), d_status, s.n * 4, cudaMemcpyDeviceToHost, s.st)) != QB3CU_OK) {
             rc = QB3CU_ERR_CUDA;
             break;

@@ -802,9 +802,21 @@ template <typename T> static cudaError_t launch_fused(const DecArgs &a, cudaStre
         smem = layout(spc);
     }
     pl.spc = spc;
-    err = dense ? allow_max_smem<decode_kernel<T, true>>() : allow_max_smem<decode_kernel<T, false>>();
+    /* Streams are dealt to the rebuild warps for good (a stream's running values pass from unit to unit inside one warp),
+       so a unit takes as long as the warp with the most streams: where eleven warps have a stream less than eight,
+       and the rebuild is what the CTA would wait for, the build with sixteen warps runs */
+    bool wide = !dense && spc > 16 && (spc + 10) / 11 < (spc + 7) / 8;
+    if (wide) {
+        pl.nwarps = 16;
+        pl.rwarps = 11;
+        smem = layout(spc);
+        if (smem > (size_t)smem_max) { wide = false; pl.nwarps = 12; pl.rwarps = 8; smem = layout(spc); }
+    }
+    err = dense ? allow_max_smem<decode_kernel<T, true>>() : wide ? allow_max_smem<decode_kernel<T, false, true>>()
+                                                                  : allow_max_smem<decode_kernel<T, false>>();
     if (err != cudaSuccess) return err;
     if (dense) decode_kernel<T, true><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
+    else if (wide) decode_kernel<T, false, true><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
     else decode_kernel<T, false><<<(a.ntiles + spc - 1) / spc, 32 * pl.nwarps, smem, st>>>(a, pl);
     launches += 1;
     return cudaGetLastError();

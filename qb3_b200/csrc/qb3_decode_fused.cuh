@@ -85,6 +85,31 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
     return v;
 }
 
+/* 8 bit data, rebuild: the sixteen values of a block (curve order, low bytes) as its four rows, a register each */
+__host__ __device__ constexpr int curve_index(uint64_t order, int n)
+{
+    for (int i = 0; i < 16; i++)
+        if ((int)((order >> (4 * (15 - i))) & 15) == n) return i;
+    return 0;
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+template <uint64_t ORDER> __device__ __forceinline__ void pack_rows(const uint32_t (&v)[16], uint32_t (&R)[4])
+{
+#define QB3_AT(n) v[std::integral_constant<int, curve_index(ORDER, n)>::value]
+    R[0] = pack4(QB3_AT(0), QB3_AT(1), QB3_AT(2), QB3_AT(3));
+    R[1] = pack4(QB3_AT(4), QB3_AT(5), QB3_AT(6), QB3_AT(7));
+    R[2] = pack4(QB3_AT(8), QB3_AT(9), QB3_AT(10), QB3_AT(11));
+    R[3] = pack4(QB3_AT(12), QB3_AT(13), QB3_AT(14), QB3_AT(15));
+#undef QB3_AT
+}
+__device__ __forceinline__ uint32_t add4(uint32_t a, uint32_t b) /* four byte sums, no carry between them */
+{
+    return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+}
+
 /* A group the fast path of the rebuild does not take: a common factor or index group, or one at the very end of the
    stream. Parsed with the general reader; v gets the sign folded values. kind: 0 plain, 1 common factor group that
    reuses the band's factor (pc_in), 2 one that wrote a new factor (returned in pc_out). */
@@ -128,8 +153,11 @@ __device__ __noinline__ void fuse_group_slow(const FuseStream &fs, uint64_t P, u
 
 /* DENSE: built for two CTAs to an SM (85 registers), for batches of more streams than one CTA per SM holds: the
    prologue and the tail of one CTA then pass behind the other's work, and a second scanner warp runs per SM. */
-template <typename T, bool DENSE = false>
-__global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid_constant__ DecArgs a, const __grid_constant__ FusePlan pl)
+/* WIDE: sixteen warps instead of twelve (128 registers), eleven of them rebuilding: with 25 to 32 streams in the CTA every
+   rebuild warp then has three streams per unit instead of four, and the scanner stops waiting for free unit slots
+   (C2 decode, 28 streams per CTA: 10.6 -> 9.3 ms). */
+template <typename T, bool DENSE = false, bool WIDE = false>
+__global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel(const __grid_constant__ DecArgs a, const __grid_constant__ FusePlan pl)
 {
     typedef typename traits<T>::W W;                     /* register type of a value */
     typedef typename std::make_signed<W>::type SW;
@@ -506,6 +534,19 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
         poff[i] = (n >> 2) * rowelems + (n & 3) * bands;
     }
     const uint32_t c4440r = pl.sel_or;
+    /* 8 bit data, up to four bands, width a multiple of four: a block's row in the staged rows is `bands` whole words. The
+       lanes of a block exchange their rows (four pixels of one band each, a register) by shuffles and every lane stores
+       one word per row: selectors that pick word lc of the interleaved row out of the bands' registers */
+    const bool simd_geo = BITS == 8 && bands <= 4 && (a.w & 3) == 0;
+    uint32_t selA = 0, selB = 0, selC = 0;
+    if (simd_geo) {
+        for (uint32_t t = 0; t < 4; t++) {
+            const uint32_t j = 4 * lc + t, x = j / bands, k = j - x * bands;
+            selA |= (k == 0 ? x : k == 1 ? 4 + x : 0u) << (4 * t);
+            selB |= (k == 2 ? x : k == 3 ? 4 + x : 0u) << (4 * t);
+            selC |= (k < 2 ? t : 4 + t) << (4 * t);
+        }
+    }
 
     for (uint32_t u = 0; u < nunits; u++) {
         const uint32_t slot = u % pl.nu, by = u / pl.upr, j = u - by * pl.upr;
@@ -520,6 +561,7 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
             const uint8_t *cb = cbs + s * bands;
             const bool ftl = fs.flags & FS_FTL, derived = fs.flags & FS_DERIVED, sweep = fs.flags & FS_SWEEP;
             const uint64_t quanta = fs.quanta;
+            const bool simd_out = simd_geo && !sweep && quanta == 1 && (fs.order == HILBERT || fs.order == ZCURVE);
             if (fs.order != poff_order) { /* hardly ever: the streams of a batch come from one encoder */
                 poff_order = fs.order;
 #pragma unroll
@@ -682,7 +724,33 @@ __global__ void __launch_bounds__(384, DENSE ? 2 : 1) decode_kernel(const __grid
                     if (active) prevS[s * bands + c] = base + tot;
                 }
                 T *p = reinterpret_cast<T *>(stage) + (size_t)(min(4 * (b0 + blk), a.w - 4) - xs) * bands + c;
-                if (sweep) {
+                bool stored = false;
+                if constexpr (BITS == 8) {
+                    if (simd_out) {
+                        uint32_t v[16], R[4];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = (uint32_t)base + (uint32_t)d[i];
+                        if (fs.order == HILBERT) pack_rows<HILBERT>(v, R);
+                        else pack_rows<ZCURVE>(v, R);
+                        if (derived) { /* the core band's pixels of the same block, four at a time (QB3decode.h:730-737) */
+                            const uint32_t dm = core != c ? 0xffffffffu : 0u, from = lane + core - c;
+#pragma unroll
+                            for (int y = 0; y < 4; y++) R[y] = add4(R[y], __shfl_sync(FULL, R[y], from) & dm);
+                        }
+                        const uint32_t l0 = lane - c;
+                        uint8_t *wp = reinterpret_cast<uint8_t *>(p) + 3 * c; /* word c of the block's row */
+#pragma unroll
+                        for (int y = 0; y < 4; y++) {
+                            const uint32_t r0 = __shfl_sync(FULL, R[y], l0), r1 = bands > 1 ? __shfl_sync(FULL, R[y], l0 + 1) : 0u;
+                            const uint32_t r2 = bands > 2 ? __shfl_sync(FULL, R[y], l0 + 2) : 0u, r3 = bands > 3 ? __shfl_sync(FULL, R[y], l0 + 3) : 0u;
+                            const uint32_t wv = __byte_perm(__byte_perm(r0, r1, selA), __byte_perm(r2, r3, selB), selC);
+                            if (active) *reinterpret_cast<uint32_t *>(wp + y * rowpitch) = wv;
+                        }
+                        stored = true;
+                    }
+                }
+                if (stored) { }
+                else if (sweep) {
                     if (active) {
 #pragma unroll
                         for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i]);

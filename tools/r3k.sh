@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests -m gpu -x -q -k "not pipe and not cli and not packaging and not dropin" 2>&1 | tail -3
+B="python bench.py --no-cpu-baseline --no-e2e --no-others"
+for t in 4096 4700 2900 1024; do echo -n "c2 $t: "; timeout 300 $B --workload c2 --tiles $t --steps 5 --warmup 3 2>/dev/null | grep -o '"decode_ms": [0-9.]*'; done

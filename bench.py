@@ -19,7 +19,7 @@ import sys
 import threading
 import time
 
-# many CUDA streams are in flight at once (host pipeline, two pass decode): more hardware queues than the default 8,
+# many CUDA streams are in flight at once (the host pipeline's chunks): more hardware queues than the default 8,
 # or streams share queues and wait for each other. Read when the CUDA context is created.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
@@ -575,8 +575,7 @@ def main():
         enc_bytes = raw_rank + comp_bytes
         enc_gbs_hbm = enc_bytes / (enc_ms * 1e-3) / 1e9
         dec_gbs_hbm = enc_bytes / (dec_ms * 1e-3) / 1e9
-        dec_kernels = "decode_kernel" if ts <= 2 else "scan_wide_kernel+rebuild_kernel"
-        dominant = "encode_kernel" if enc_ms >= dec_ms else dec_kernels
+        dominant = "encode_kernel" if enc_ms >= dec_ms else "decode_kernel"
         traffic = ncu_traffic(wl, ntiles, dominant)
         dom_ach = enc_gbs_hbm if enc_ms >= dec_ms else dec_gbs_hbm
         line = {

@@ -225,6 +225,33 @@ def test_batch_full_size_properties():
         assert dst[t, :sizes_h[t]].cpu().numpy().tobytes() == want
 
 
+@pytest.mark.parametrize("mode", [MODE_BASE, MODE_BEST])
+def test_batch_full_size_config3(mode):
+    """BASELINE config 3 at full size: 1024 Landsat-like tiles of 512x512x8 u16, core band 0, BASE and BEST. Every tile
+    round trips, eight tiles spread over the batch are byte-identical to the oracle's streams, and the size-only pass
+    agrees with the encode on all 1024 sizes."""
+    torch = torch_mod()
+    n, w, h, b = 1024, 512, 512, 8
+    from bench import device_synth_tiles
+    src = device_synth_tiles(n, w, h, b, 2, torch.device("cuda"))
+    cfg = q.config(w, h, b, 2, mode=mode, cband=[0] * b)
+    dst, sizes, status = q.encode_batch(cfg, src, n)
+    offsets = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+    out, st = q.decode_batch(cfg, dst, offsets, sizes, n)
+    only = q.encoded_size_batch(cfg, src, n)
+    torch.cuda.synchronize()
+    assert not status.any().item() and not st.any().item()
+    assert torch.equal(out.view(-1), src.view(-1))
+    assert torch.equal(only, sizes)
+    sizes_h = sizes.cpu().numpy()
+    O = oracle()
+    for t in (0, 1, 127, 300, 511, 777, 1022, 1023):
+        tile = synth_tiles(1, w, h, b, np.uint16, t0=t)[0]
+        assert np.array_equal(src[t].cpu().numpy().view(np.uint16).reshape(h, w, b), tile)  # device generator == host generator
+        want = O.encode(tile, mode=mode, cband=[0] * b)
+        assert sizes_h[t] == len(want) and dst[t, :sizes_h[t]].cpu().numpy().tobytes() == want, "tile %d" % t
+
+
 def test_batch_decode_reports_bad_streams():
     torch = torch_mod()
     tiles = synth_tiles(4, 32, 32, 1, np.uint8)

@@ -499,7 +499,9 @@ __global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel
         for (;;) {
             /* chunks up to AHEAD beyond the one being read; as many rounds as the lane that is furthest behind needs */
             const uint32_t want = vcons[lane] + 1 + AHEAD;
-            const uint32_t rounds = __reduce_max_sync(0xffffffffu, want - issued);
+            /* not for less than eight chunks of the lane that is furthest behind (the ring is 62 ahead, the scanner asks
+               for 17): the feeder shares its scheduler with rebuild warps */
+            const uint32_t lag = __reduce_max_sync(0xffffffffu, want - issued), rounds = lag >= 8 ? lag : 0;
 #pragma unroll 1
             for (uint32_t q = 0; q < rounds; q++) request(issued < want);
             cp_async_commit();
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel
             vfill[lane] = before;
             before = issued;
             if (*(volatile uint32_t *)&feed_done) break;
-            if (rounds == 0) __nanosleep(256);
+            if (rounds == 0) __nanosleep(512);
         }
         cp_async_wait<0>();
         return;

@@ -1300,12 +1300,15 @@ __device__ static uint64_t rle_sync(const uint8_t *p, uint64_t n, uint64_t from)
 /* One CTA per tile, after encode_kernel, for the RLE modes only: RLE when it pays, else the stored check
    (reference: QB3encode.cpp:536-573). */
 constexpr uint32_t RLE_THREADS = 512, RLE_MAXCHUNKS = 2048;
-__global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant__ EncArgs a, uint32_t ntiles)
+/* blockDim and maxch (the chunk tables in dynamic shared memory) follow the size a stream can have: a batch of 64 x 64
+   tiles gets two warps and a dozen table entries per tile, not sixteen warps and 16 KB */
+__global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant__ EncArgs a, uint32_t ntiles, uint32_t maxch)
 {
-    __shared__ uint32_t sync_s[RLE_MAXCHUNKS + 1]; /* chunk starts; streams are far below 4 GB (max_size / 2 of a 64K x 64K tile is not) */
-    __shared__ uint32_t size_s[RLE_MAXCHUNKS];
-    __shared__ uint32_t scratch[36];
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RLE_THREADS / 32;
+    extern __shared__ __align__(16) uint32_t rle_smem[];
+    uint32_t *sync_s = rle_smem;                 /* [maxch + 1] chunk starts; streams are far below 4 GB */
+    uint32_t *size_s = sync_s + maxch + 1;       /* [maxch] */
+    uint32_t *scratch = size_s + maxch;          /* [36] */
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT / 32;
     uint8_t *dst = a.dst + (uint64_t)tile * a.slot;
     const uint8_t *src = a.src + (uint64_t)tile * a.src_pitch;
     if (dst[10] == M_STORED) return; /* already final */
@@ -1313,9 +1316,9 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant_
     if (len <= a.max_size / 2 && data < 0xffffffffull) { /* "a vague limit", but it decides the bytes */
         const uint64_t avail = a.max_size - len;
         const uint8_t *p = dst + hdr;
-        /* chunks of at least 1 KB, at most RLE_MAXCHUNKS of them */
+        /* chunks of at least 1 KB, at most maxch of them */
         uint64_t csize = 1024;
-        while ((data + csize - 1) / csize > RLE_MAXCHUNKS) csize *= 2;
+        while ((data + csize - 1) / csize > maxch) csize *= 2;
         const uint32_t nch = (uint32_t)((data + csize - 1) / csize);
         for (uint32_t k = warp; k < nch; k += nwarps) {
             const uint64_t s = rle_sync(p, data, k * csize);
@@ -1329,9 +1332,9 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant_
             if (lane == 0) size_s[k] = (uint32_t)z;
         }
         __syncthreads();
-        /* exclusive scan of the chunk sizes, RLE_THREADS at a time */
+        /* exclusive scan of the chunk sizes, a CTA's worth at a time */
         uint64_t rsz = 0;
-        for (uint32_t k0 = 0; k0 < nch; k0 += RLE_THREADS) {
+        for (uint32_t k0 = 0; k0 < nch; k0 += NT) {
             const uint32_t k = k0 + tid, v = k < nch ? size_s[k] : 0u;
             uint32_t total;
             const uint32_t off = block_exclusive_scan(v, scratch, total);
@@ -1347,7 +1350,7 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant_
             }
             __syncthreads();
             /* down over the data: the output is shorter than the data, so the two ranges do not overlap */
-            for (uint64_t k = tid; k < rsz; k += RLE_THREADS) dst[hdr + k] = dst[len + k];
+            for (uint64_t k = tid; k < rsz; k += NT) dst[hdr + k] = dst[len + k];
             if (tid == 0) {
                 dst[10] = (uint8_t)a.rle_mode;
                 a.sizes[tile] = hdr + rsz;
@@ -1359,8 +1362,8 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_kernel(const __grid_constant_
         const uint32_t ts = a.raw_size / ((uint64_t)a.w * a.h * a.bands);
         const uint64_t line = (uint64_t)a.w * a.bands * ts, pitch = a.stride * ts;
         __syncthreads();
-        for (uint32_t i = tid; i < a.hdr_stored_len; i += RLE_THREADS) dst[i] = a.hdr_stored[i];
-        for (uint64_t i = tid; i < a.raw_size; i += RLE_THREADS) {
+        for (uint32_t i = tid; i < a.hdr_stored_len; i += NT) dst[i] = a.hdr_stored[i];
+        for (uint64_t i = tid; i < a.raw_size; i += NT) {
             const uint64_t y = i / line, x = i - y * line;
             dst[a.hdr_stored_len + i] = src[y * pitch + x];
         }
@@ -1474,7 +1477,12 @@ static cudaError_t launch_rle(const EncArgs &a, size_t ntiles, cudaStream_t st)
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     /* streams of less than 64 KB are a handful of chunks: nothing to share */
     if (ntiles >= (size_t)2 * nsm || a.max_size / 2 < 65536) {
-        rle_kernel<<<(unsigned)ntiles, RLE_THREADS, 0, st>>>(a, (uint32_t)ntiles);
+        /* a warp for every 4 KB a stream can have when RLE is tried at all, a table entry for every 1 KB */
+        const uint64_t most = a.max_size / 2;
+        uint32_t maxch = (uint32_t)(most / 1024 + 2 < RLE_MAXCHUNKS ? most / 1024 + 2 : RLE_MAXCHUNKS);
+        uint32_t threads = (uint32_t)(32 * ((most + 4095) / 4096) < RLE_THREADS ? 32 * ((most + 4095) / 4096) : RLE_THREADS);
+        if (threads < 32) threads = 32;
+        rle_kernel<<<(unsigned)ntiles, threads, (2 * maxch + 1 + 36) * 4, st>>>(a, (uint32_t)ntiles, maxch);
         return cudaGetLastError();
     }
     RleWide w;

@@ -120,6 +120,12 @@ def test_api_quanta_stride_state():
     a = P.encode(small, mode=MODE_BASE, reps=2)
     assert a == O.encode(small, mode=MODE_BASE, reps=2) and a[0] == a[1]
     assert np.array_equal(P.decode(a[1]), small)
+    # ... and for an image large enough to be coded in parts, BEST included: the second call starts from the values,
+    # rungs and common factors the first one left behind
+    big = (synth_tiles(1, 640, 512, 3, np.uint8)[0] >> 2) * np.uint8(5)
+    for mode in (MODE_BASE, MODE_CF_H, MODE_BEST):
+        a = P.encode(big, mode=mode, reps=2)
+        assert a == O.encode(big, mode=mode, reps=2), "mode %d" % mode
 
 
 def test_api_small_and_many_bands():

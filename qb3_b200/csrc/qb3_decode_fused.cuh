@@ -751,17 +751,18 @@ __global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel
                         stored = true;
                     }
                 }
-                if (stored) { }
-                else if (sweep) {
-                    if (active) {
+                /* the scattered stores of the lanes named by `mine` */
+                auto put_block = [&](bool mine) {
+                    if (sweep) {
+                        if (mine) {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i]);
+                            for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i]);
+                        }
+                        return;
                     }
-                }
-                else {
                     /* core bands first, then the derived bands add their core band's pixels: the same 16 places, one
                        band over (QB3decode.h:730-737) */
-                    if (active && core == c) {
+                    if (mine && core == c) {
                         if (quanta > 1) {
 #pragma unroll
                             for (int i = 0; i < 16; i++)
@@ -774,12 +775,25 @@ __global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel
                     }
                     if (derived) {
                         __syncwarp();
-                        if (active && core != c) {
+                        if (mine && core != c) {
                             const T *q = p + (int)core - (int)c;
 #pragma unroll
                             for (int i = 0; i < 16; i++) p[poff[i]] = (T)(base + (W)d[i] + q[poff[i]]);
                         }
                     }
+                };
+                if (!stored) {
+                    /* A width that is not a multiple of four moves the row's last block back over the one before it, and
+                       the reference writes block after block: the last block's pixels are the ones that stay
+                       (QB3decode.h:603-737). The two agree on every stream an encoder wrote; on a damaged stream they need
+                       not, and the device decodes those like the reference, pixel for pixel. */
+                    const bool moved = (a.w & 3) != 0 && b0 + blk == nbx - 1;
+                    if (__any_sync(FULL, active && moved)) {
+                        put_block(active && !moved);
+                        __syncwarp();
+                        put_block(active && moved);
+                    }
+                    else put_block(active);
                 }
                 __syncwarp();
             }

@@ -1145,10 +1145,8 @@ __global__ void __launch_bounds__(256) stitch_kernel(const __grid_constant__ Enc
     }
     const unsigned long long len = lens[part], end = start + len;
     const uint32_t *in = reinterpret_cast<const uint32_t *>(a.tmp + ((uint64_t)tile * a.parts + part) * a.tmp_slot);
-    const uint32_t *prev = part ? reinterpret_cast<const uint32_t *>(a.tmp + ((uint64_t)tile * a.parts + part - 1) * a.tmp_slot) : nullptr;
-    const unsigned long long plen = part ? lens[part - 1] : 0;
     uint32_t *out = reinterpret_cast<uint32_t *>(dst);
-    const uint32_t sh = (uint32_t)start & 31;           /* bits of the first word that belong to the part before */
+    const uint32_t sh = (uint32_t)start & 31;           /* bits of the first word that belong to the parts before */
     const unsigned long long w0 = start >> 5;
     /* words whose first bit is in [start, end), and the word start falls into when it begins inside it */
     const unsigned long long wfirst = sh ? w0 + 1 : w0, wend = (end + 31) >> 5, nin = (len + 31) >> 5;
@@ -1159,18 +1157,34 @@ __global__ void __launch_bounds__(256) stitch_kernel(const __grid_constant__ Enc
         const uint32_t hi = r && i + 1 >= 0 && (unsigned long long)(i + 1) < nin ? in[i + 1] : 0u;
         return r ? (lo >> r) | (hi << (32 - r)) : lo;
     };
-    if (sh && tid == 0 && len) { /* the shared word: the last sh bits of the part before, then this part's first bits */
-        const unsigned long long pb = plen - sh; /* parts are thousands of bits long */
-        const uint32_t r = (uint32_t)pb & 31;
-        const unsigned long long i = pb >> 5, pn = (plen + 31) >> 5;
-        const uint32_t lo = prev[i], hi = r && i + 1 < pn ? prev[i + 1] : 0u;
-        const uint32_t tail = (r ? (lo >> r) | (hi << (32 - r)) : lo) & ((1u << sh) - 1);
-        out[w0] = tail | (in[0] << sh);
+    if (len) {
+        if (sh && tid == 0) {
+            /* The shared word, from whatever parts have bits in it: usually the tail of the part before and the head
+               of this one, but a part can be a few bits or none at all (a BEST part whose groups the reference's
+               encoder drops, QB3encode.h:704-708), so every part is asked. */
+            uint32_t v = 0;
+            unsigned long long qs = 0;
+            for (uint32_t q = 0; q < a.parts; q++) {
+                const unsigned long long ql = lens[q], lo = 32 * w0 > qs ? 32 * w0 : qs, hi = 32 * w0 + 32 < qs + ql ? 32 * w0 + 32 : qs + ql;
+                if (lo < hi) {
+                    const uint32_t *pin = reinterpret_cast<const uint32_t *>(a.tmp + ((uint64_t)tile * a.parts + q) * a.tmp_slot);
+                    const unsigned long long o = lo - qs, i = o >> 5, pn = (ql + 31) >> 5;
+                    const uint32_t r = (uint32_t)o & 31, n = (uint32_t)(hi - lo);
+                    const uint32_t x0 = pin[i], x1 = r && i + 1 < pn ? pin[i + 1] : 0u;
+                    const uint32_t bits = (r ? (x0 >> r) | (x1 << (32 - r)) : x0) & (n < 32 ? (1u << n) - 1 : ~0u);
+                    v |= bits << (uint32_t)(lo - 32 * w0);
+                }
+                qs += ql;
+            }
+            out[w0] = v;
+        }
+        /* a word that ends beyond this part belongs to the next part that has bits, unless there is none */
+        bool more = false;
+        for (uint32_t q = part + 1; q < a.parts; q++) more |= lens[q] != 0;
+        const unsigned long long wstop = (more && (end & 31)) ? end >> 5 : wend;
+        for (unsigned long long w = wfirst + tid; w < wstop; w += NT)
+            out[w] = word_at((long long)(32 * w) - (long long)start);
     }
-    /* a word that ends beyond this part belongs to the next one, unless this is the last part */
-    const unsigned long long wstop = (part + 1 < a.parts && (end & 31)) ? end >> 5 : wend;
-    for (unsigned long long w = wfirst + tid; w < wstop; w += NT)
-        out[w] = word_at((long long)(32 * w) - (long long)start);
     if (part == 0 && tid == 0) {
         a.sizes[tile] = len_bytes;
         if (a.status) a.status[tile] = 0;

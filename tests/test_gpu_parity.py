@@ -663,6 +663,42 @@ def test_rle_by_chunks_matches_oracle(kind, shape, dt, mode):
     assert np.array_equal(out.cpu().numpy().view(dt).reshape(tiles.shape), tiles)
 
 
+def test_streams_the_reference_encoder_breaks():
+    """In the common factor modes the reference drops a 64 bit group of more than 800 bits for an empty index group
+    (QB3encode.h:704-708). The streams are the reference's byte for byte all the same -- down to a tile in parts whose
+    parts hold no bits at all -- and decode like the reference decodes them: failure where it fails, and where it
+    does not, the same (meaningless) pixels, which at a width that is not a multiple of four depends on the moved-back
+    last block of a row being written after the one it overlaps. Found by tools/fuzz.py."""
+    torch = torch_mod()
+    O = oracle()
+    # every group dropped: the stream is its headers; three parts, two of them empty
+    tiles = np.stack([content("highrung", 71, 93, 2, np.int64, seed=s) for s in (3, 4, 5)])
+    kw = dict(mode=MODE_CF, quanta=37)
+    cfg, dst, sizes, status = encode_tiles(tiles, **kw)
+    sz, d = sizes.cpu().numpy(), dst.cpu().numpy()
+    for t in range(3):
+        want = O.encode(tiles[t], **kw)
+        assert len(want) < 64 and int(sz[t]) == len(want) and d[t, :sz[t]].tobytes() == want
+    # some groups dropped, the decoder runs on regardless
+    checked = 0
+    for seed in range(1, 7):
+        for dt, kw in ((np.int64, dict(mode=MODE_BEST, quanta=5, away=True)), (np.uint64, dict(mode=MODE_CF_H, quanta=5))):
+            img = content("fewvals", 9, 62, 1, dt, seed=seed)
+            cfg, dst, sizes, status = encode_tiles(img[None], **kw)
+            want = O.encode(img, **kw)
+            assert dst.cpu().numpy()[0, :int(sizes[0])].tobytes() == want
+            offsets = torch.zeros(1, device="cuda", dtype=torch.int64)
+            out, st = q.decode_batch(cfg, dst, offsets, sizes, 1)
+            torch.cuda.synchronize()
+            ref = O.decode(want)
+            if ref is None:
+                assert int(st[0]) != 0
+            else:
+                assert int(st[0]) == 0 and np.array_equal(out[0].cpu().numpy().view(dt).reshape(img.shape), ref)
+                checked += not np.array_equal(ref, img)
+    assert checked > 0   # at least one stream that decodes, and not to what went in
+
+
 @pytest.mark.parametrize("dt,mode", [(np.uint8, MODE_BASE), (np.uint8, MODE_BEST), (np.uint16, MODE_BEST), (np.int32, MODE_BASE),
                                      (np.uint8, MODE_FTL), (np.uint64, MODE_BEST), (np.int16, MODE_BASE), (np.int8, 1)])
 def test_damaged_streams_decode_like_the_oracle(dt, mode):

@@ -33,6 +33,8 @@ while time.time() < t_end:
         continue
     mode = int(rng.integers(0, 9))
     n = int(rng.choice([1, 2, 3, 7, 33])) if not big else int(rng.choice([1, 2, 5]))
+    if not big and rng.random() < 0.08 and w * h * b * dt.itemsize <= 40000:
+        n = int(rng.choice([2500, 3000, 4500, 5000, 9000]))   # 17 to 32 streams per CTA, and more than one CTA per SM holds
     kw = dict(mode=mode)
     if rng.random() < 0.4:                        # band map: a few core bands, the others derived from them
         cores = rng.choice(b, size=max(1, b // 3), replace=False)
@@ -44,8 +46,9 @@ while time.time() < t_end:
         kw["quanta"] = int(rng.choice([2, 3, 4, 5, 10, 37]))
         kw["away"] = bool(rng.integers(0, 2))
     kind = CONTENT_KINDS[rng.integers(0, len(CONTENT_KINDS))]
-    tiles = np.stack([content(kind, w, h, b, dt, seed=int(rng.integers(1, 1 << 30))) if i % 2 == 0
-                      else synth_tiles(1, w, h, b, dt, seed=int(rng.integers(1, 1 << 30)))[0] for i in range(n)])
+    few = [content(kind, w, h, b, dt, seed=int(rng.integers(1, 1 << 30))) if i % 2 == 0
+           else synth_tiles(1, w, h, b, dt, seed=int(rng.integers(1, 1 << 30)))[0] for i in range(min(n, 34))]
+    tiles = np.stack([few[i % len(few)] for i in range(n)])   # a large batch repeats its first 34 tiles
     desc = "dt=%s w=%d h=%d b=%d n=%d kind=%s kw=%r" % (dt.name, w, h, b, n, kind, kw)
     try:
         cfg = q.config(w, h, b, dtype_code(dt), **kw)

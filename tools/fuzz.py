@@ -3,7 +3,10 @@ size drawn at random; every case is encoded (qb3cu_encode_batch), measured (qb3c
 (qb3cu_decode_batch) on the device, and the streams of its first and last tile are compared byte for byte with
 oracle/qb3_oracle.c. Prints the failing configuration and stops at the first difference.
 
-  python tools/fuzz.py [--seconds 120] [--seed 1]
+  python tools/fuzz.py [--seconds 120] [--seed 1] [--api]
+
+--api: the same draw through the QB3.h calls instead (one image per handle, band maps as the caller would give them,
+encoded twice on the handle so that its running state is carried, decoded through qb3_read_start / _info / _data).
 """
 import argparse, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,11 +14,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import qb3_b200 as q
-from helpers import CONTENT_KINDS, DTYPES, content, dtype_code, oracle, synth_tiles
+from helpers import CONTENT_KINDS, DTYPES, PRODUCT_SO, QB3Lib, content, dtype_code, oracle, synth_tiles
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=120)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--api", action="store_true")
 args = ap.parse_args()
 rng = np.random.default_rng(args.seed)
 O = oracle()
@@ -45,18 +49,42 @@ while time.time() < t_end:
     if rng.random() < 0.25:
         kw["quanta"] = int(rng.choice([2, 3, 4, 5, 10, 37]))
         kw["away"] = bool(rng.integers(0, 2))
+    if mode >= 4 and rng.random() < 0.1:          # an arbitrary 4x4 scan curve, written as an "SC" chunk
+        perm = rng.permutation(16)
+        kw["order"] = int(sum(int(v) << (4 * (15 - i)) for i, v in enumerate(perm)))
+    packed_decode = rng.random() < 0.3            # decode from the packed blob instead of the slots
     kind = CONTENT_KINDS[rng.integers(0, len(CONTENT_KINDS))]
     few = [content(kind, w, h, b, dt, seed=int(rng.integers(1, 1 << 30))) if i % 2 == 0
            else synth_tiles(1, w, h, b, dt, seed=int(rng.integers(1, 1 << 30)))[0] for i in range(min(n, 34))]
     tiles = np.stack([few[i % len(few)] for i in range(n)])   # a large batch repeats its first 34 tiles
-    desc = "dt=%s w=%d h=%d b=%d n=%d kind=%s kw=%r" % (dt.name, w, h, b, n, kind, kw)
+    desc = "dt=%s w=%d h=%d b=%d n=%d kind=%s packed=%s kw=%r" % (dt.name, w, h, b, n, kind, packed_decode, kw)
+    if args.api:
+        if b > 16 or "order" in kw:               # the header's QB3_MAXBANDS; the API has no setter for the curve
+            continue
+        try:
+            P = P if "P" in globals() else QB3Lib(PRODUCT_SO, 16)
+            got, want = P.encode(tiles[0], reps=2, **kw), O.encode(tiles[0], reps=2, **kw)
+            assert got == want, "qb3_encode differs from the oracle (%d, %d vs %d, %d bytes)" % (len(got[0]), len(got[1]), len(want[0]), len(want[1]))
+            for sbytes in want:
+                ref, back = O.decode(sbytes), P.decode(sbytes)
+                assert (ref is None) == (back is None), "qb3_read_data %s where the oracle %s" % ("fails" if back is None else "succeeds", "fails" if ref is None else "succeeds")
+                assert ref is None or np.array_equal(ref, back), "qb3_read_data gives other pixels than the oracle"
+        except Exception as exc:  # noqa: BLE001
+            print("FAILED after %d cases: %s\n  %s: %s" % (ncases, desc, type(exc).__name__, exc), flush=True)
+            sys.exit(1)
+        ncases += 1
+        continue
     try:
         cfg = q.config(w, h, b, dtype_code(dt), **kw)
         src = torch.from_numpy(np.ascontiguousarray(tiles).view(np.uint8).reshape(n, -1)).cuda()
         dst, sizes, st = q.encode_batch(cfg, src, n)
         only = q.encoded_size_batch(cfg, src, n)
-        off = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
-        out, st2 = q.decode_batch(cfg, dst, off, sizes, n)
+        if packed_decode:
+            blob, off, total = q.pack_streams(dst, sizes, n)
+            out, st2 = q.decode_batch(cfg, blob, off, sizes, n)
+        else:
+            off = torch.arange(n, device="cuda", dtype=torch.int64) * dst.stride(0)
+            out, st2 = q.decode_batch(cfg, dst, off, sizes, n)
         torch.cuda.synchronize()
         assert not st.any().item(), "encode status"
         sz, d = sizes.cpu().numpy(), dst.cpu().numpy()

@@ -435,25 +435,29 @@ __global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel
                             z = __funnelshift_r(ring[wi & (RWORDS - 1)], wa, at);
                             zh = __funnelshift_r(wa, wb, at);
                         };
-                        if (RARE && BITS == 16 && r == 15 && !special) {
-                            /* two 17 bit codes do not fit a window, so the walk above may have gone wrong: again, a value at a
-                               time; rare */
-                            reopen(gpos);
-                            next_window(z, zh, 0, swl);
+                        /* the two rare cases behind one branch: a rarely taken branch costs its reconvergence point on every
+                           group (~25 cycles), and 16 bit data had two of them */
+                        if (RARE && (special || (BITS == 16 && r == 15))) {
+                            if (!special) {
+                                /* two 17 bit codes do not fit a window, so the walk above may have gone wrong: again, a value
+                                   at a time */
+                                reopen(gpos);
+                                next_window(z, zh, 0, swl);
     #pragma unroll 1
-                            for (int i = 0; i < 16; i++) next_window(z, zh, 0, code_len(lens, z));
-                        }
-                        if (special) { /* common factor or index group: parsed in full from the ring, it is rare */
-                            RingBits<RWORDS> t;
-                            t.ring = ring;
-                            t.pos = gpos + swl;
-                            W sg[16];
-                            uint8_t rbv = (uint8_t)oldrung;
-                            W pc = pcfs[c * 32 + lane];
-                            failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
-                            pcfs[c * 32 + lane] = pc;
-                            r = rbv;
-                            reopen(t.pos);
+                                for (int i = 0; i < 16; i++) next_window(z, zh, 0, code_len(lens, z));
+                            }
+                            else { /* common factor or index group: parsed in full from the ring */
+                                RingBits<RWORDS> t;
+                                t.ring = ring;
+                                t.pos = gpos + swl;
+                                W sg[16];
+                                uint8_t rbv = (uint8_t)oldrung;
+                                W pc = pcfs[c * 32 + lane];
+                                failed |= read_special_group<W, BITS, U>(t, sg, rbv, pc);
+                                pcfs[c * 32 + lane] = pc;
+                                r = rbv;
+                                reopen(t.pos);
+                            }
                         }
                         rbs[c * 32 + lane] = (uint8_t)r;
                         c = cnext;

@@ -366,7 +366,10 @@ __global__ void __launch_bounds__(WIDE ? 512 : 384, DENSE ? 2 : 1) decode_kernel
                        ring is valid as far as it can get before the next upkeep */
                     upkeep(pos);
                     const uint32_t gn = min((uint32_t)EVERY, ng - g0);
-    #pragma unroll 1
+                    /* two groups to a turn of the loop where it was measured to pay (8 bit FTL, the twelve warp build:
+                       8.8 -> 8.5 ms; every other build lost by it) */
+                    constexpr int TURN = (BITS == 8 && !RARE && !WIDE && !DENSE) ? 2 : 1;
+    #pragma unroll(TURN)
                     for (uint32_t gi = 0; gi < gn; gi++) {
                         const uint32_t oldrung = rung_next, e = e_next;
                         const uint32_t gpos = pos;
